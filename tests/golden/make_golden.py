@@ -1,0 +1,199 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference from /root/reference on CPU fp32.
+
+Run in the dev container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own, so these files are the pin for
+both the oracle (oracle/*.py) and the CUDA path.  Nothing is copied from the reference: it is imported
+in-place with the two shims of SURVEY.md Appendix B (kornia stub, torchvision weight download disabled).
+
+Files written
+  kitti_sample.npz        bundled KITTI sample (example/test_monorec.py: keyframe 169, frames 168/170):
+                          uint8 inputs + reference CostVolumeModule outputs (sub-sampled volumes, full argmax,
+                          valid masks, per-plane float64 checksums)
+  cv_synth_small.npz      full reference cost-volume tensors for small seeded synthetic configs
+  model_synth_small.npz   full MonoRecModel forward (seeded weights, 2 gains) on a small synthetic config:
+                          cv_mask, 4 depth maps, image_features checksums
+"""
+import os
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+REF = Path(os.environ.get("MONOREC_REFERENCE", "/root/reference"))
+sys.path.insert(0, str(REPO))
+
+from monorec_b200.synthetic import make_inputs, seeded_state_dict  # noqa: E402
+
+
+def import_reference():
+    """SURVEY.md Appendix B shims, then import the reference's model module."""
+    for name in ["kornia", "kornia.augmentation", "kornia.geometry", "kornia.geometry.camera", "kornia.geometry.depth"]:
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["kornia.augmentation"].RandomHorizontalFlip = object
+    sys.modules["kornia.augmentation"].RandomResizedCrop = object
+    sys.modules["kornia.geometry.camera"].pixel2cam = None
+    sys.modules["kornia.geometry.depth"].DepthWarper = None
+    sys.modules["kornia"].augmentation = sys.modules["kornia.augmentation"]
+    import torchvision
+    orig = torchvision.models.resnet18
+    torchvision.models.resnet18 = lambda pretrained=False, **kw: orig(weights=None)
+    sys.path.insert(0, str(REF))
+    import model.monorec.monorec_model as ref_mod  # noqa
+    return ref_mod
+
+
+def load_kitti_sample():
+    """Restates the example loader for the single bundled sample.
+
+    reference: example/test_monorec.py:18-45, data_loader/kitti_odometry_dataset.py:120-134 (crop, resize, /255-.5),
+    :253-269 (frame selection), :318-374 (intrinsics).  Returns uint8 CHW images + float32 matrices.
+    """
+    from PIL import Image
+    root = REF / "example" / "data" / "kitti"
+    calib = {}
+    for line in open(root / "sequences" / "07" / "calib.txt"):
+        k, v = line.split(":", 1)
+        calib[k] = np.array([float(x) for x in v.split()])
+    P2 = calib["P2"].reshape(3, 4)
+    H, W = 256, 512
+    img0 = Image.open(root / "sequences" / "07" / "image_2" / "000169.png")
+    ow, oh = img0.size
+    r_orig, r_target = oh / ow, H / W
+    assert r_orig < r_target
+    new_w = oh / r_target
+    box = ((ow - new_w) // 2, 0, ow - (ow - new_w) // 2, oh)
+    c_x = (P2[0, 2] - (ow - new_w) / 2) / new_w
+    c_y = P2[1, 2] / oh
+    rescale = oh / H
+    f_x = P2[0, 0] / W / rescale
+    f_y = P2[1, 1] / H / rescale
+    K = np.zeros((4, 4), np.float32)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2], K[2, 2], K[3, 3] = f_x * W, f_y * H, c_x * W, c_y * H, 1, 1
+    poses_all = np.loadtxt(root / "poses_dvso" / "07.txt").reshape(-1, 3, 4)
+
+    def pose(i):
+        p = np.eye(4, dtype=np.float32)
+        p[:3] = poses_all[i]
+        return p
+
+    def image(i):
+        im = Image.open(root / "sequences" / "07" / "image_2" / f"{i:06d}.png").crop(box)
+        im = im.resize((W, H), resample=Image.BILINEAR)
+        return np.array(im).transpose(2, 0, 1).copy()  # uint8 CHW
+
+    return {"keyframe_u8": image(169), "frames_u8": np.stack([image(168), image(170)]), "K": K,
+            "keyframe_pose": pose(169), "poses": np.stack([pose(168), pose(170)]), "crop_box": np.array(box)}
+
+
+def sample_to_dict(s):
+    to_t = lambda u8: (torch.from_numpy(u8.astype(np.float32)) / 255 - .5)
+    nF = s["frames_u8"].shape[0]
+    return {"keyframe": to_t(s["keyframe_u8"]).unsqueeze(0),
+            "keyframe_pose": torch.from_numpy(s["keyframe_pose"]).unsqueeze(0),
+            "keyframe_intrinsics": torch.from_numpy(s["K"]).unsqueeze(0),
+            "frames": [to_t(s["frames_u8"][i]).unsqueeze(0) for i in range(nF)],
+            "poses": [torch.from_numpy(s["poses"][i]).unsqueeze(0) for i in range(nF)],
+            "intrinsics": [torch.from_numpy(s["K"]).unsqueeze(0) for _ in range(nF)]}
+
+
+def run_ref_cv(ref_mod, data, steps=32, inv=(0.33, 0.0025)):
+    cvm = ref_mod.CostVolumeModule()
+    d = dict(data)
+    key = d["keyframe"]
+    d["inv_depth_min"] = key.new_tensor([inv[0]])
+    d["inv_depth_max"] = key.new_tensor([inv[1]])
+    d["cv_depth_steps"] = key.new_tensor([steps], dtype=torch.int32)
+    with torch.no_grad():
+        d = cvm(d)
+    return d["cost_volume"], d["single_frame_cvs"]
+
+
+def top2_margin(cv):
+    t = torch.topk(cv, 2, dim=1)[0]
+    return (t[:, 0] - t[:, 1])
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ref_mod = import_reference()
+
+    # ---- 1. bundled KITTI sample --------------------------------------------------------------
+    s = load_kitti_sample()
+    data = sample_to_dict(s)
+    cv, sf = run_ref_cv(ref_mod, data)
+    # the same reference in float64 (for the tie-margin rule of SURVEY.md §8c)
+    data64 = {k: ([t.double() for t in v] if isinstance(v, list) else v.double()) for k, v in data.items()}
+    torch.set_default_dtype(torch.float64)
+    cv64, sf64 = run_ref_cv(ref_mod, data64)
+    torch.set_default_dtype(torch.float32)
+    print("kitti sample: fp32 vs fp64 reference max|d| =", float((cv.double() - cv64).abs().max()),
+          "argmax agree =", float((cv.argmax(1) == cv64.argmax(1)).float().mean()))
+    sub = (slice(None), slice(None), slice(2, None, 4), slice(1, None, 8))
+    np.savez_compressed(
+        HERE / "kitti_sample.npz",
+        keyframe_u8=s["keyframe_u8"], frames_u8=s["frames_u8"], K=s["K"], keyframe_pose=s["keyframe_pose"],
+        poses=s["poses"],
+        cv_sub=cv[sub].numpy(), sf_sub=np.stack([v[sub].numpy() for v in sf]),
+        cv_rows=cv[:, :, 100:104].numpy(), sf_rows=np.stack([v[:, :, 100:104].numpy() for v in sf]),
+        argmax=cv.argmax(1).numpy().astype(np.uint8),
+        margin=top2_margin(cv).numpy().astype(np.float16),
+        margin64=top2_margin(cv64).numpy().astype(np.float16),
+        argmax64=cv64.argmax(1).numpy().astype(np.uint8),
+        cv_zero=np.packbits((cv == 0).all(1).numpy()),
+        sf_zero=np.packbits(np.stack([(v == 0).all(1).numpy() for v in sf])),
+        cv_plane_sum=cv.double().sum((2, 3)).numpy(), sf_plane_sum=np.stack([v.double().sum((2, 3)).numpy() for v in sf]),
+        cv_plane_sqsum=(cv.double() ** 2).sum((2, 3)).numpy(),
+    )
+
+    # ---- 2. small synthetic cost volumes (full tensors) ---------------------------------------
+    small = {}
+    for tag, (B, nF, D, H, W, seed) in {"a": (2, 2, 32, 32, 64, 1), "b": (1, 3, 16, 40, 72, 2),
+                                        "c": (1, 4, 32, 48, 64, 3)}.items():
+        d = make_inputs(B, nF, H, W, seed=seed)
+        cv, sf = run_ref_cv(ref_mod, d, steps=D)
+        small[f"{tag}_cfg"] = np.array([B, nF, D, H, W, seed])
+        small[f"{tag}_cv"] = cv.numpy()
+        small[f"{tag}_sf"] = np.stack([v.numpy() for v in sf])
+        small[f"{tag}_key_u8"] = np.round((d["keyframe"].numpy() + 0.5) * 255).astype(np.uint8)
+        small[f"{tag}_frames_u8"] = np.round((torch.stack(d["frames"]).numpy() + 0.5) * 255).astype(np.uint8)
+        small[f"{tag}_poses"] = torch.stack(d["poses"]).numpy()
+        small[f"{tag}_K"] = d["keyframe_intrinsics"].numpy()
+    np.savez_compressed(HERE / "cv_synth_small.npz", **small)
+
+    # ---- 3. full model on a small synthetic config --------------------------------------------
+    out = {}
+    B, nF, H, W, seed = 1, 2, 64, 128, 5
+    for gain_tag, gain in (("g1", 1.0), ("g07", 0.7)):
+        model = ref_mod.MonoRecModel()
+        model.load_state_dict(seeded_state_dict(model, seed=7, gain=gain))
+        model.eval()
+        d = make_inputs(B, nF, H, W, seed=seed)
+        with torch.no_grad():
+            r = model(d)
+        out[f"{gain_tag}_cv_mask"] = r["cv_mask"].numpy()
+        for i, p in enumerate(r["predicted_inverse_depths"]):
+            out[f"{gain_tag}_depth{i}"] = p.numpy()
+        for i, p in enumerate(r["image_features"]):
+            out[f"{gain_tag}_feat{i}_sum"] = np.array([p.double().sum().item(), p.double().abs().sum().item()])
+        out[f"{gain_tag}_cost_volume_masked_sum"] = np.array([r["cost_volume"].double().sum().item()])
+        q = torch.tensor([0.01, 0.25, 0.5, 0.75, 0.99])
+        print(gain_tag, "result q", torch.quantile(r["result"].flatten(), q), "mask q", torch.quantile(r["cv_mask"].flatten(), q))
+        print(gain_tag, "result range", float(r["result"].min()), float(r["result"].max()),
+              "mask range", float(r["cv_mask"].min()), float(r["cv_mask"].max()))
+    out["cfg"] = np.array([B, nF, 32, H, W, seed, 7])
+    np.savez_compressed(HERE / "model_synth_small.npz", **out)
+    for f in sorted(HERE.glob("*.npz")):
+        print(f.name, f.stat().st_size // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,46 @@
+"""The oracle restatements vs the golden vectors minted from the reference itself (CPU, no GPU needed)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cost_volume_oracle as O
+from tests.helpers import compare_volumes, kitti_sample_dict, synth_small_dict
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_torch_restatement_matches_reference_small(tag):
+    data, D, ref_cv, ref_sf = synth_small_dict(tag)
+    cv, sf = O.cost_volume_torch(data, steps=D)
+    # same primitives, same order: should be (nearly) bit-identical to the reference
+    assert (cv - ref_cv).abs().max().item() <= 5e-5
+    for a, r in zip(sf, ref_sf):
+        assert (a - r).abs().max().item() <= 5e-5
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_closed_form_matches_reference_small(tag):
+    data, D, ref_cv, ref_sf = synth_small_dict(tag)
+    cv, sf, valid, _ = O.cost_volume_closed_form(data, steps=D, dtype=np.float32)
+    stats = compare_volumes(torch.from_numpy(cv), [torch.from_numpy(s) for s in sf], ref_cv, ref_sf)
+    print(tag, stats)
+
+
+def test_torch_restatement_matches_reference_kitti():
+    data, g = kitti_sample_dict()
+    cv, sf = O.cost_volume_torch(data)
+    sub = (slice(None), slice(None), slice(2, None, 4), slice(1, None, 8))
+    # fp32 SSIM variance terms cancel catastrophically (SURVEY.md §7 hard part 2): a different BLAS summation
+    # order in the projection already moves the volume by ~1e-4, so the gate is the north-star 1e-3, reported.
+    d = np.abs(cv[sub].numpy() - g["cv_sub"]).max()
+    print("kitti torch-restatement max|d| =", d)
+    assert d <= 3e-4
+    for i, v in enumerate(sf):
+        assert np.abs(v[sub].numpy() - g["sf_sub"][i]).max() <= 3e-4
+    assert (cv.argmax(1).numpy().astype(np.uint8) == g["argmax"]).mean() > 0.999
+    np.testing.assert_allclose(cv.double().sum((2, 3)).numpy(), g["cv_plane_sum"], rtol=0, atol=5e-2)
+
+
+def test_plane_depths_order():
+    z = O.plane_depths(0.33, 0.0025, 32)
+    assert abs(z[0].item() - 400.0) < 1e-2 and abs(z[-1].item() - 1 / 0.33) < 1e-5
+    assert torch.all(z[1:] < z[:-1])
