@@ -1,0 +1,96 @@
+/*
+ * monorec_b200.h -- C ABI of libmonorec_b200.so (sm_100a kernels for MonoRec's hot path).
+ *
+ * The reference (Brummi/MonoRec) is pure Python/PyTorch and has no FFI of its own; these entry points are
+ * what a binding for the hot path replaces.  Every entry point cites the reference code it
+ * stands in for.  Conventions:
+ *   - plain C types only; device pointers are owned by the caller (PyTorch allocates inputs and outputs);
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - return 0 on success, a negative MR_E* code or a positive cudaError_t otherwise;
+ *     mr_last_error() returns a thread-local message for the last failure;
+ *   - no global mutable state: callable concurrently from several host threads on different devices.
+ * All tensors are contiguous fp32 unless stated; image-like tensors are NCHW like the reference's.
+ */
+#ifndef MONOREC_B200_H
+#define MONOREC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_OK 0
+#define MR_EINVAL -1      /* bad argument (shape, null pointer, unsupported option) */
+#define MR_ENOSUPPORT -2  /* valid reference option that this library does not implement */
+#define MR_ENOMEM -3      /* workspace too small */
+
+#define MR_MAX_FRAMES 8   /* source frames per keyframe (reference configs use 2..4, BASELINE config 5 uses 6) */
+
+/* Library / build identification: (major<<16 | minor<<8 | patch). */
+int mr_version(void);
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* mr_last_error(void);
+/* Number of kernels this library has launched from the calling thread since the last reset (for bench.py's
+ * `gpu_launches`); mr_launch_count(1) resets after reading. */
+long long mr_launch_count(int reset);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Projection tables.  Replaces torch.inverse / matmul at model/monorec/monorec_model.py:171,198,207 and
+ * model/layers.py:65 (point_projection): for every (batch b, source frame f)
+ *     P = (K_f . inv(pose_f) . pose_kf)[0:3, 0:4],   Kinv = inv(K_kf)[0:3, 0:3]
+ *     proj[b,f] = [ P[:, :3] . Kinv | P[:, 3] ]      (3x4 row-major, fp32, evaluated in fp64 on device)
+ * with row 0 scaled by W/(W-1), row 1 by H/(H-1) (the reference's normalise-with-(W-1) / sample-with-W quirk,
+ * layers.py:67-68 + F.grid_sample default align_corners=False) and 1e-7 added to P[2,3] (layers.py:66), so that
+ * for a keyframe pixel (u,v) and plane depth z:   c = proj[:, :3] . [u, v, 1] * z + proj[:, 3]
+ *     source pixel  sx = c.x / c.z - 0.5,   sy = c.y / c.z - 0.5 .
+ * keyframe_pose, keyframe_K: [B,4,4]; poses[f], intrinsics[f]: host arrays of F device pointers, each [B,4,4].
+ * depths (optional, may be NULL): writes 1/linspace(inv_depth_lo, inv_depth_hi, D) to depths[D]
+ * (monorec_model.py:184-185; lo = data_dict["inv_depth_max"] = 0.0025, hi = data_dict["inv_depth_min"] = 0.33).
+ * No host synchronisation.
+ */
+int mr_projection_tables(const float* keyframe_pose, const float* keyframe_K,
+                         const float* const* poses, const float* const* intrinsics,
+                         int B, int F, int H, int W,
+                         float* proj /* [B,F,3,4] */,
+                         float* depths /* [D] or NULL */, int D, float inv_depth_lo, float inv_depth_hi,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused plane-sweep cost volume.  Replaces CostVolumeModule.forward, model/monorec/monorec_model.py:150-280
+ * (use_ssim=True, sfcv_mult_mask=True, not_center_cv=False, patch_size=3; SSIM = model/layers.py:119-137):
+ * per-plane homography warp with bilinear zero-padded sampling, 3x3 SSIM, channel-weighted 3x3 patch cost,
+ * validity mask, per-frame view weighting and multi-frame fusion, in one kernel without intermediate tensors.
+ *   keyframe      [B,3,H,W]
+ *   frames        host array of F device pointers, each [B,3,H,W]
+ *   proj          [B,F,3,4] from mr_projection_tables
+ *   depths        [D] plane depths (index 0 = farthest)
+ *   out_cv        [B,D,H,W]      data_dict["cost_volume"]
+ *   out_sfcv      [F,B,D,H,W]    data_dict["single_frame_cvs"][f] = out_sfcv[f]
+ *   alpha         view-weight sharpness (reference: 10), chan_w[3] channel weights (reference: 5/32,16/32,11/32)
+ * Constraints: 1 <= F <= MR_MAX_FRAMES, 2 <= D <= 128, H >= 5, W >= 5.
+ */
+int mr_cost_volume_fwd(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
+                       float* out_cv, float* out_sfcv,
+                       int B, int F, int D, int H, int W,
+                       float alpha, const float* chan_w /* host, 3 floats, NULL = reference default */,
+                       void* stream);
+
+/* Same path with HOST buffers (pinned or pageable): uploads the images and matrices, runs
+ * mr_projection_tables + mr_cost_volume_fwd and downloads both volumes; batch elements are pipelined on
+ * internal streams so copies overlap the kernel.  This is the end-to-end entry bench.py times as `e2e`.
+ *   h_keyframe [B,3,H,W]; h_frames [F,B,3,H,W]; h_keyframe_pose,h_keyframe_K [B,4,4]; h_poses,h_intrinsics [F,B,4,4]
+ *   h_out_cv [B,D,H,W]; h_out_sfcv [F,B,D,H,W]
+ * workspace: device buffer of at least mr_cost_volume_host_workspace(B,F,D,H,W) bytes (caller-owned).
+ */
+long long mr_cost_volume_host_workspace(int B, int F, int D, int H, int W);
+int mr_cost_volume_host(const float* h_keyframe, const float* h_frames,
+                        const float* h_keyframe_pose, const float* h_keyframe_K,
+                        const float* h_poses, const float* h_intrinsics,
+                        float* h_out_cv, float* h_out_sfcv,
+                        int B, int F, int D, int H, int W,
+                        float inv_depth_lo, float inv_depth_hi, float alpha,
+                        void* workspace, long long workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONOREC_B200_H */

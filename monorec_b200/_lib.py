@@ -1,0 +1,67 @@
+"""ctypes binding of libmonorec_b200.so (the C ABI declared in include/monorec_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmonorec_b200.so"
+_lib = None
+
+c_float_p = POINTER(c_float)
+
+# name -> (restype, argtypes); mirrors include/monorec_b200.h one to one (tests/test_capi_symbols.py checks it)
+SIGNATURES = {
+    "mr_version": (c_int, []),
+    "mr_last_error": (c_char_p, []),
+    "mr_launch_count": (c_longlong, [c_int]),
+    "mr_projection_tables": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int,
+                                     c_int, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
+    "mr_cost_volume_fwd": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_int, c_float, c_float_p, c_void_p]),
+    "mr_cost_volume_host_workspace": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
+    "mr_cost_volume_host": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float] * 3 + [c_void_p, c_longlong]),
+}
+
+
+class MonorecLibraryError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """Returns the loaded CDLL.  Builds it in-tree with nvcc if absent and a compiler is available."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists() and build_if_missing:
+        from . import build as _build
+        _build.build()
+    if not LIB_PATH.exists():
+        raise MonorecLibraryError(f"{LIB_PATH} not found: run `python -m monorec_b200.build` (needs nvcc, sm_100a)")
+    lib = ctypes.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mr_last_error().decode(errors="replace")
+        raise MonorecLibraryError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr_array(tensors):
+    """Host array of device (or host) pointers for the `const float* const*` parameters."""
+    arr = (c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def launch_count(reset=False):
+    return int(load().mr_launch_count(1 if reset else 0))
