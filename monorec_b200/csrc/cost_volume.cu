@@ -21,13 +21,21 @@
 // tile are skipped.
 #include "mr_common.cuh"
 #include <cstdint>
+#include <type_traits>
 
 namespace {
 
 constexpr int kTileCols = 64;   // buffer columns per tile row (output columns + 2-px halo each side)
 constexpr int kOutCols = 60;    // output columns per tile
 constexpr int kRowStride = 68;  // floats per smem image row: column b lives at index b+1 (so [2l-1, 2l+2] is 8B aligned)
-constexpr int kThreads = 512;
+#ifndef MR_CV_THREADS
+#define MR_CV_THREADS 512
+#endif
+constexpr int kThreads = MR_CV_THREADS;
+#ifndef MR_CV_MINBLOCKS
+#define MR_CV_MINBLOCKS 1      // resident CTAs per SM the register allocator must leave room for
+#endif
+
 constexpr int kWarps = kThreads / 32;
 constexpr float kC1 = 0.01f * 0.01f;  // layers.py:116
 constexpr float kC2 = 0.03f * 0.03f;  // layers.py:117
@@ -45,48 +53,64 @@ struct CvArgs {
 };
 
 struct SmemLayout {
-    int sad, ytile, cst, xbuf, wts, zs, vmask, misc, total;  // byte offsets
+    int ytile, cst, xbuf, pjs, zs, vmask, rowrng, total;  // byte offsets
 };
 
 __host__ __device__ inline SmemLayout make_layout(int D, int TH, int F) {
     SmemLayout L;
     int off = 0;
-    L.sad = off;   off += D * TH * kTileCols * 4;
     L.ytile = off; off += 3 * (TH + 4) * kRowStride * 4;
     L.cst = off;   off += 3 * (TH + 2) * kTileCols * 8;
     L.xbuf = off;  off += kWarps * 3 * kRowStride * 4;
-    L.wts = off;   off += F * TH * kTileCols * 4;
+    L.pjs = off;   off += F * 12 * 4;
     L.zs = off;    off += ((D + 3) / 4) * 16;
-    L.vmask = off; off += TH * kTileCols;
-    L.misc = off;  off += 16;
+    L.vmask = off; off += F * TH * kTileCols;
+    L.rowrng = off; off += F * 2 * 4;
     L.total = off;
     return L;
 }
 
-__device__ __forceinline__ float ssim_err(float s1, float sxx, float sxy, float mu_y, float sy2) {
-    // layers.py:123-137 with the 3x3 means expressed through box sums; mu_y and sy2 = sigma_y + C2 are hoisted.
-    const float k9 = 1.0f / 9.0f;
-    float mu_x = s1 * k9;
-    float mxy = mu_x * mu_y;
-    float mxx = mu_x * mu_x;
-    float sig_xy = fmaf(sxy, k9, -mxy);
-    float sig_x = fmaf(sxx, k9, -mxx);
-    float n = fmaf(2.0f, mxy, kC1) * fmaf(2.0f, sig_xy, kC2);
-    float d = (mxx + fmaf(mu_y, mu_y, kC1)) * (sig_x + sy2);
-    float q = __fdividef(n, d);
-    return __saturatef(fmaf(-0.5f, q, 0.5f));
+// ---- packed fp32x2 helpers (FADD2 / FMUL2 / FFMA2 on sm_100a; a pair is either two columns or two samples) ----------
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+// single MUFU.RCP (flush-to-zero variant: no denormal pre/post-scaling code; operands here are never denormal)
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) cost_volume_kernel(const CvArgs a) {
+__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+constexpr int kChunk = 32;                 // planes the per-pixel phase keeps in registers at once
+constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
+constexpr int kMagicBits = 0x4B400000;
+
+// SSIM numerator / denominator for a pair of columns (layers.py:123-134 through 3x3 box sums; mu_y, sigma_y + C2 hoisted)
+__device__ __forceinline__ void ssim_nd(float2 s1, float2 sxx, float2 sxy, float2 mu_y, float2 sy2, float2& n, float2& d) {
+    const float2 k9 = bc2(1.0f / 9.0f);
+    float2 mu_x = mul2(s1, k9);
+    float2 mxy = mul2(mu_x, mu_y);
+    float2 mxx = mul2(mu_x, mu_x);
+    float2 sig_xy = fma2(sxy, k9, neg2(mxy));
+    float2 sig_x = fma2(sxx, k9, neg2(mxx));
+    n = mul2(fma2(bc2(2.0f), mxy, bc2(kC1)), fma2(bc2(2.0f), sig_xy, bc2(kC2)));
+    d = mul2(add2(mxx, fma2(mu_y, mu_y, bc2(kC1))), add2(sig_x, sy2));
+}
+
+__global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(const CvArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = make_layout(a.D, a.TH, a.F);
-    float* sad_s = reinterpret_cast<float*>(smem + L.sad);
     float* ytile = reinterpret_cast<float*>(smem + L.ytile);
     float* cst = reinterpret_cast<float*>(smem + L.cst);
-    float* wts = reinterpret_cast<float*>(smem + L.wts);
+    float* pjs = reinterpret_cast<float*>(smem + L.pjs);
     float* zs = reinterpret_cast<float*>(smem + L.zs);
     unsigned char* vmask = smem + L.vmask;
-    int* misc = reinterpret_cast<int*>(smem + L.misc);
+    int* rowrng = reinterpret_cast<int*>(smem + L.rowrng);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W, D = a.D, TH = a.TH, F = a.F;
@@ -94,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_kernel(const CvArgs a
     const int u0 = blockIdx.x * kOutCols - 2;  // image column of buffer column 0
     const int v0 = blockIdx.y * TH;            // image row of tile row 0
     const size_t plane = (size_t)H * W;
+    const int planei = H * W;
     float* xbuf = reinterpret_cast<float*>(smem + L.xbuf) + warp * 3 * kRowStride;
 
     // ---- keyframe tile (+0.5, monorec_model.py:232) and hoisted SSIM terms -------------------------------------
@@ -108,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_kernel(const CvArgs a
     for (int i = tid; i < D; i += kThreads) zs[i] = __ldg(a.depths + i);
     if (lane < 3) { xbuf[lane * kRowStride] = 0.f; xbuf[lane * kRowStride + kTileCols + 1] = 0.f; }
     __syncthreads();
+    // table entry for the column pair (2j, 2j+1) of e-row er, channel ch: (mu_y[2j], mu_y[2j+1], sy2[2j], sy2[2j+1])
     for (int i = tid; i < 3 * (TH + 2) * kTileCols; i += kThreads) {
         int bc = i % kTileCols, t = i / kTileCols, er = t % (TH + 2), ch = t / (TH + 2);
         const float* y = ytile + (ch * (TH + 4) + er) * kRowStride + bc;  // rows er..er+2, idx bc..bc+2
@@ -122,216 +148,285 @@ __global__ void __launch_bounds__(kThreads, 1) cost_volume_kernel(const CvArgs a
             }
         float mu = s1 * (1.0f / 9.0f);
         float sy2 = fmaf(s2, 1.0f / 9.0f, -mu * mu) + kC2;
-        reinterpret_cast<float2*>(cst)[(ch * (TH + 2) + er) * kTileCols + bc] = make_float2(mu, sy2);
+        float* dst = cst + ((ch * (TH + 2) + er) * (kTileCols / 2) + (bc >> 1)) * 4 + (bc & 1);
+        dst[0] = mu;
+        dst[2] = sy2;
     }
 
     const float fW = (float)W, fH = (float)H;
     const float sx_lo = -(fW + 1.f) * 0.5f, sx_hi = (3.f * fW - 1.f) * 0.5f;  // == grid clamp(-2, 2), monorec_model.py:208
     const float sy_lo = -(fH + 1.f) * 0.5f, sy_hi = (3.f * fH - 1.f) * 0.5f;
+    const float2 fu2 = make_float2((float)(u0 + lane), (float)(u0 + lane + 32));
+    const float2 cw0 = bc2(a.cw0), cw1 = bc2(a.cw1), cw2 = bc2(a.cw2);
+    // per-lane smem bases for stage 2 (columns 2l-1 .. 2l+2 live at float index 2l .. 2l+3 of a row)
+    const float* xs_l = xbuf + 2 * lane;
+    const float* ys_l = ytile + 2 * lane;
+    const float4* cs_l = reinterpret_cast<const float4*>(cst) + lane;
+    const int ych = (TH + 4) * kRowStride;        // ytile channel stride (floats)
+    const int cch = (TH + 2) * (kTileCols / 2);   // cst channel stride (float4)
+    // stage 2 writes the single-frame volume for output columns u0 + 2l, u0 + 2l + 1 (lanes 1..30)
+    const int ucol = u0 + 2 * lane;
+    const bool st0 = (lane >= 1) && (lane <= 30) && (ucol < W);
+    const bool st1 = (lane >= 1) && (lane <= 30) && (ucol + 1 < W);
+    const bool st_pair = st0 && st1 && ((W & 1) == 0);
 
-    for (int f = 0; f < F; ++f) {
-        const float* pj = a.proj + ((size_t)b * F + f) * 12;
-        const float m00 = __ldg(pj + 0), m01 = __ldg(pj + 1), m02 = __ldg(pj + 2), m03 = __ldg(pj + 3);
-        const float m10 = __ldg(pj + 4), m11 = __ldg(pj + 5), m12 = __ldg(pj + 6), m13 = __ldg(pj + 7);
-        const float m20 = __ldg(pj + 8), m21 = __ldg(pj + 9), m22 = __ldg(pj + 10), m23 = __ldg(pj + 11);
-        const float* img = a.frames[f] + (size_t)b * 3 * plane;
-
-        if (tid == 0) { misc[0] = TH; misc[1] = -1; }
-        __syncthreads();  // also orders the previous frame's phase 2 before sad/vmask are overwritten
-
-        // ---- validity pre-pass: valid_f(v,u) = interior(v,u) & all_d [ sample strictly inside (1,W-2)x(1,H-2) ] ----
-        // (monorec_model.py:212-219: bilinear sample of the interior mask != 0 for every plane)
-        for (int p = tid; p < TH * kTileCols; p += kThreads) {
-            int r = p >> 6, bc = p & 63;
-            int u = u0 + bc, v = v0 + r;
-            bool ok = (bc >= 2) && (bc < 2 + kOutCols) && (u >= 2) && (u < W - 2) && (v >= 2) && (v < H - 2);
-            if (ok) {
-                float fu = (float)u, fv = (float)v;
-                float ax = fmaf(m00, fu, fmaf(m01, fv, m02));
-                float ay = fmaf(m10, fu, fmaf(m11, fv, m12));
-                float az = fmaf(m20, fu, fmaf(m21, fv, m22));
-                for (int d = 0; d < D; ++d) {
-                    float z = zs[d];
-                    float cz = fmaf(az, z, m23);
-                    float inv = __fdividef(1.0f, cz);
-                    float sx = fmaf(fmaf(ax, z, m03), inv, -0.5f);
-                    float sy = fmaf(fmaf(ay, z, m13), inv, -0.5f);
-                    ok = ok && (sx > 1.0f) && (sx < fW - 2.0f) && (sy > 1.0f) && (sy < fH - 2.0f);
-                }
-            }
-            vmask[p] = ok ? 1 : 0;
-            if (ok) { atomicMin(&misc[0], r); atomicMax(&misc[1], r); }
-        }
-        __syncthreads();
-        const int rlo = misc[0], rhi = misc[1];
-
-        // ---- march: one plane per warp at a time -------------------------------------------------------------------
-        if (rhi >= rlo) {
-            for (int d = warp; d < D; d += kWarps) {
+    // ---- validity pre-pass for every frame: valid_f(v,u) = interior(v,u) & all_d [ sample strictly inside
+    //      (1,W-2)x(1,H-2) ]  (monorec_model.py:212-219: bilinear sample of the interior mask != 0 for every plane) ----
+    if (tid < 2 * F) rowrng[tid] = (tid & 1) ? -1 : TH;
+    if (tid < 12 * F) pjs[tid] = __ldg(a.proj + (size_t)b * F * 12 + tid);
+    __syncthreads();
+    for (int q = tid; q < F * TH * kTileCols; q += kThreads) {
+        const int f = q / (TH * kTileCols), p = q - f * (TH * kTileCols);
+        const int r = p >> 6, bc = p & 63;
+        const int u = u0 + bc, v = v0 + r;
+        bool ok = (bc >= 2) && (bc < 2 + kOutCols) && (u >= 2) && (u < W - 2) && (v >= 2) && (v < H - 2);
+        if (ok) {
+            const float* m = pjs + 12 * f;
+            const float fu = (float)u, fv = (float)v;
+            const float ax = fmaf(m[0], fu, fmaf(m[1], fv, m[2]));
+            const float ay = fmaf(m[4], fu, fmaf(m[5], fv, m[6]));
+            const float az = fmaf(m[8], fu, fmaf(m[9], fv, m[10]));
+            const float m03 = m[3], m13 = m[7], m23 = m[11];
+            for (int d = 0; d < D; ++d) {
                 const float z = zs[d];
-                float h1a[3][2], h1b[3][2], hxa[3][2], hxb[3][2], hya[3][2], hyb[3][2];
-                float hEa[2], hEb[2];
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) h1a[c][j] = h1b[c][j] = hxa[c][j] = hxb[c][j] = hya[c][j] = hyb[c][j] = 0.f;
-                hEa[0] = hEa[1] = hEb[0] = hEb[1] = 0.f;
-
-                const int nsteps = rhi - rlo + 5;
-                for (int t = 0; t < nsteps; ++t) {
-                    const int r = rlo - 2 + t;  // tile-relative row of the warped row produced in this step
-                    // ---------- stage 1: warp one row (lane = column, two rounds) ----------
-                    {
-                        const float fv = (float)(v0 + r);
-                        const float rx = fmaf(m01, fv, m02), ry = fmaf(m11, fv, m12), rz = fmaf(m21, fv, m22);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int bc = lane + 32 * k;
-                            const float fu = (float)(u0 + bc);
-                            float cx = fmaf(fmaf(m00, fu, rx), z, m03);
-                            float cy = fmaf(fmaf(m10, fu, ry), z, m13);
-                            float cz = fmaf(fmaf(m20, fu, rz), z, m23);
-                            float inv = __fdividef(1.0f, cz);
-                            float sx = fminf(fmaxf(fmaf(cx, inv, -0.5f), sx_lo), sx_hi);
-                            float sy = fminf(fmaxf(fmaf(cy, inv, -0.5f), sy_lo), sy_hi);
-                            float x0f = floorf(sx), y0f = floorf(sy);
-                            float wx1 = sx - x0f, wy1 = sy - y0f;
-                            float wx0 = (x0f + 1.0f) - sx, wy0 = (y0f + 1.0f) - sy;
-                            int x0 = (int)x0f, y0 = (int)y0f;
-                            // zero padding: taps outside the image contribute 0 (F.grid_sample padding_mode="zeros")
-                            if ((unsigned)x0 >= (unsigned)W) wx0 = 0.f;
-                            if ((unsigned)(x0 + 1) >= (unsigned)W) wx1 = 0.f;
-                            if ((unsigned)y0 >= (unsigned)H) wy0 = 0.f;
-                            if ((unsigned)(y0 + 1) >= (unsigned)H) wy1 = 0.f;
-                            int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
-                            int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
-                            float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
-                            const float* p0 = img + (size_t)ya * W;
-                            const float* p1 = img + (size_t)yb * W;
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                float i00 = __ldg(p0 + c * plane + xa), i01 = __ldg(p0 + c * plane + xb);
-                                float i10 = __ldg(p1 + c * plane + xa), i11 = __ldg(p1 + c * plane + xb);
-                                float val = i00 * w00;
-                                val = fmaf(i01, w01, val);
-                                val = fmaf(i10, w10, val);
-                                val = fmaf(i11, w11, val);
-                                xbuf[c * kRowStride + bc + 1] = val + 0.5f;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    // ---------- stage 2: lane owns buffer columns 2l, 2l+1 ----------
-                    float E[2] = {0.f, 0.f};
-                    {
-                        const float* yrow = ytile + (r + 2) * kRowStride + 2 * lane;
-                        const float* crow = cst + ((size_t)r * kTileCols + 2 * lane) * 2;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            float2 xl = *reinterpret_cast<const float2*>(xbuf + c * kRowStride + 2 * lane);
-                            float2 xr = *reinterpret_cast<const float2*>(xbuf + c * kRowStride + 2 * lane + 2);
-                            float2 yl = *reinterpret_cast<const float2*>(yrow + c * (TH + 4) * kRowStride);
-                            float2 yr = *reinterpret_cast<const float2*>(yrow + c * (TH + 4) * kRowStride + 2);
-                            // columns 2l-1, 2l, 2l+1, 2l+2
-                            float mid1 = xl.y + xr.x;
-                            float h1_0 = xl.x + mid1, h1_1 = mid1 + xr.y;
-                            float xx0 = xl.x * xl.x, xx1 = xl.y * xl.y, xx2 = xr.x * xr.x, xx3 = xr.y * xr.y;
-                            float midx = xx1 + xx2;
-                            float hx_0 = xx0 + midx, hx_1 = midx + xx3;
-                            float xy0 = xl.x * yl.x, xy1 = xl.y * yl.y, xy2 = xr.x * yr.x, xy3 = xr.y * yr.y;
-                            float midy = xy1 + xy2;
-                            float hy_0 = xy0 + midy, hy_1 = midy + xy3;
-                            if (t >= 2) {
-                                float4 k4 = *reinterpret_cast<const float4*>(crow + (size_t)c * (TH + 2) * kTileCols * 2);
-                                float cw = (c == 0) ? a.cw0 : ((c == 1) ? a.cw1 : a.cw2);
-                                float e0 = ssim_err(h1a[c][0] + h1b[c][0] + h1_0, hxa[c][0] + hxb[c][0] + hx_0,
-                                                    hya[c][0] + hyb[c][0] + hy_0, k4.x, k4.y);
-                                float e1 = ssim_err(h1a[c][1] + h1b[c][1] + h1_1, hxa[c][1] + hxb[c][1] + hx_1,
-                                                    hya[c][1] + hyb[c][1] + hy_1, k4.z, k4.w);
-                                E[0] = fmaf(cw, e0, E[0]);
-                                E[1] = fmaf(cw, e1, E[1]);
-                            }
-                            h1a[c][0] = h1b[c][0]; h1b[c][0] = h1_0; h1a[c][1] = h1b[c][1]; h1b[c][1] = h1_1;
-                            hxa[c][0] = hxb[c][0]; hxb[c][0] = hx_0; hxa[c][1] = hxb[c][1]; hxb[c][1] = hx_1;
-                            hya[c][0] = hyb[c][0]; hyb[c][0] = hy_0; hya[c][1] = hyb[c][1]; hyb[c][1] = hy_1;
-                        }
-                    }
-                    if (t >= 2) {
-                        float eL = __shfl_up_sync(0xffffffffu, E[1], 1);
-                        float eR = __shfl_down_sync(0xffffffffu, E[0], 1);
-                        float mid = E[0] + E[1];
-                        float hE0 = eL + mid, hE1 = mid + eR;
-                        if (t >= 4) {
-                            float2 s = make_float2(hEa[0] + hEb[0] + hE0, hEa[1] + hEb[1] + hE1);
-                            *reinterpret_cast<float2*>(sad_s + ((size_t)d * TH + (r - 2)) * kTileCols + 2 * lane) = s;
-                        }
-                        hEa[0] = hEb[0]; hEb[0] = hE0; hEa[1] = hEb[1]; hEb[1] = hE1;
-                    }
-                    __syncwarp();
-                }
+                const float inv = fast_rcp(fmaf(az, z, m23));
+                const float sx = fmaf(fmaf(ax, z, m03), inv, -0.5f);
+                const float sy = fmaf(fmaf(ay, z, m13), inv, -0.5f);
+                ok = ok && (sx > 1.0f) && (sx < fW - 2.0f) && (sy > 1.0f) && (sy < fH - 2.0f);
             }
         }
-        __syncthreads();
-
-        // ---- phase 2: per-pixel view weight and single-frame volume (monorec_model.py:250-260) -------------------
-        float* sf_out = a.sfcv + ((size_t)f * a.B + b) * D * plane;
-        for (int p = tid; p < TH * kTileCols; p += kThreads) {
-            int r = p >> 6, bc = p & 63;
-            int u = u0 + bc, v = v0 + r;
-            bool own = (bc >= 2) && (bc < 2 + kOutCols) && (u < W) && (v < H);
-            if (!own) continue;
-            const bool valid = vmask[p] != 0;
-            float w = 0.f;
-            float* out = sf_out + (size_t)v * W + u;
-            if (valid) {
-                const float* s = sad_s + (size_t)r * kTileCols + bc;
-                float m = s[0];
-                for (int d = 1; d < D; ++d) m = fminf(m, s[(size_t)d * TH * kTileCols]);
-                float sum = 0.f;
-                for (int d = 0; d < D; ++d) {
-                    float sv = s[(size_t)d * TH * kTileCols];
-                    float df = sv - m;
-                    sum += __expf(-a.alpha * df * df);
-                    out[(size_t)d * plane] = fmaf(-2.0f, sv, 1.0f);
-                }
-                // weight = 1 - 1/(D-1) * (sum - 1): separate roundings as in the reference so that flat-cost pixels
-                // (sum == D) give exactly 0 (monorec_model.py:258, :265-269)
-                w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
-            } else {
-                for (int d = 0; d < D; ++d) out[(size_t)d * plane] = 0.f;
-            }
-            wts[f * TH * kTileCols + p] = w;
-        }
+        vmask[q] = ok ? 1 : 0;
+        if (ok) { atomicMin(&rowrng[2 * f], r); atomicMax(&rowrng[2 * f + 1], r); }
     }
     __syncthreads();
 
-    // ---- fusion (monorec_model.py:262-269): cv = sum_f w_f (1 - 2 sad_f) / sum_f w_f, 0 where sum_f w_f == 0 -----
-    for (int p = tid; p < TH * kTileCols; p += kThreads) {
-        int r = p >> 6, bc = p & 63;
-        int u = u0 + bc, v = v0 + r;
-        bool own = (bc >= 2) && (bc < 2 + kOutCols) && (u < W) && (v < H);
-        if (!own) continue;
-        float wf[MR_MAX_FRAMES];
-        float wsum = 0.f;
+    // ---- march: the F*D (frame, plane) units are dealt round-robin to the warps; no CTA-wide barrier in here --------
+    for (int unit = warp; unit < F * D; unit += kWarps) {
+        const int f = unit / D, d = unit - f * D;
+        const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
+        if (rhi < rlo) continue;  // no valid pixel of this tile for frame f: phase 2 zero-fills
+        const float* m = pjs + 12 * f;
+        const float* img = a.frames[f] + (size_t)b * 3 * plane;
+        const float z = zs[d];
+        const int nsteps = rhi - rlo + 5;
+        // projection c = M [u v 1]^T z + p split into a per-lane column part and a per-row part
+        const float2 pzx = mul2(mul2(bc2(m[0]), fu2), bc2(z)), pzy = mul2(mul2(bc2(m[4]), fu2), bc2(z)),
+                     pzz = mul2(mul2(bc2(m[8]), fu2), bc2(z));
+        const float rax = m[1] * z, rbx = fmaf(m[2], z, m[3]);
+        const float ray = m[5] * z, rby = fmaf(m[6], z, m[7]);
+        const float raz = m[9] * z, rbz = fmaf(m[10], z, m[11]);
+        // rolling state: horizontal 3-sums of X, X^2, XY per channel (pair = columns 2l, 2l+1) for the last rows,
+        // indexed by (row step mod 3) so that no register moves are needed
+        float2 hs1[3][3], hsx[3][3], hsy[3][3], hE[3];
 #pragma unroll
-        for (int f = 0; f < MR_MAX_FRAMES; ++f) {
-            wf[f] = (f < F) ? wts[f * TH * kTileCols + p] : 0.f;
-            wsum += wf[f];
+        for (int i = 0; i < 3; ++i) {
+            hE[i] = bc2(0.f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) hs1[i][c] = hsx[i][c] = hsy[i][c] = bc2(0.f);
         }
-        float* out = a.cv + (size_t)b * D * plane + (size_t)v * W + u;
-        if (wsum == 0.f) {
-            for (int d = 0; d < D; ++d) out[(size_t)d * plane] = 0.f;
-        } else {
-            const float inv = 1.0f / wsum;
-            const float* sf = a.sfcv + (size_t)b * D * plane + (size_t)v * W + u;
-            const size_t fstride = (size_t)a.B * D * plane;
-            for (int d = 0; d < D; ++d) {
-                float num = 0.f;
+        float* out_d = a.sfcv + (((size_t)f * a.B + b) * D + d) * plane + (size_t)v0 * W + ucol;
+
+        auto row_step = [&](auto phase_tag, const int t) {
+            constexpr int P = decltype(phase_tag)::value;
+            constexpr int P1 = (P + 1) % 3, P2 = (P + 2) % 3;
+            const int r = rlo - 2 + t;  // tile-relative row of the warped row produced in this step
+            // ---------- stage 1: homography of the row (pair = columns lane, lane + 32), 24 bilinear taps ----------
+            {
+                const float fv = (float)(v0 + r);
+                const float rcx = fmaf(rax, fv, rbx), rcy = fmaf(ray, fv, rby), rcz = fmaf(raz, fv, rbz);
+                const float2 cx = add2(pzx, bc2(rcx)), cy = add2(pzy, bc2(rcy)), cz = add2(pzz, bc2(rcz));
+                const float2 inv = make_float2(fast_rcp(cz.x), fast_rcp(cz.y));
+                const float2 ux = mul2(cx, inv), uy = mul2(cy, inv);
+                // floor by magic-number rounding: rn(s - 0.5) differs from floor(s) only for integral s, where the
+                // interpolated value is the same (weight 1 on the tap both conventions share)
+                const float2 tx = add2(ux, bc2(kMagic - 1.0f)), ty = add2(uy, bc2(kMagic - 1.0f));
+                const int x0a = __float_as_int(tx.x) - kMagicBits, x0b = __float_as_int(tx.y) - kMagicBits;
+                const int y0a = __float_as_int(ty.x) - kMagicBits, y0b = __float_as_int(ty.y) - kMagicBits;
+                const bool inb = ((unsigned)x0a <= (unsigned)(W - 2)) && ((unsigned)x0b <= (unsigned)(W - 2)) &&
+                                 ((unsigned)y0a <= (unsigned)(H - 2)) && ((unsigned)y0b <= (unsigned)(H - 2));
+                float2 w00, w01, w10, w11;
+                int oa, ob, dxa, dxb, dya, dyb;
+                if (__all_sync(0xffffffffu, inb)) {
+                    // fast path: all 4 taps of every lane are inside the image
+                    const float2 x0f = add2(tx, bc2(-kMagic)), y0f = add2(ty, bc2(-kMagic));
+                    const float2 wx1 = add2(add2(ux, bc2(-0.5f)), neg2(x0f)), wy1 = add2(add2(uy, bc2(-0.5f)), neg2(y0f));
+                    const float2 wx0 = add2(bc2(1.0f), neg2(wx1)), wy0 = add2(bc2(1.0f), neg2(wy1));
+                    w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
+                    oa = y0a * W + x0a; ob = y0b * W + x0b;
+                    dxa = dxb = 1; dya = dyb = W;
+                } else {
+                    // border path: per-tap zero padding exactly like F.grid_sample(padding_mode="zeros"): clamp the tap
+                    // address, zero the weight of every tap that falls outside the image
+                    float wx0s[2], wx1s[2], wy0s[2], wy1s[2];
+                    int os[2], dxs[2], dys[2];
 #pragma unroll
-                for (int f = 0; f < MR_MAX_FRAMES; ++f)
-                    if (f < F && wf[f] != 0.f) num = fmaf(wf[f], __ldcg(sf + f * fstride + (size_t)d * plane), num);
-                out[(size_t)d * plane] = num * inv;
+                    for (int k = 0; k < 2; ++k) {
+                        float sxk = (k ? ux.y : ux.x) - 0.5f, syk = (k ? uy.y : uy.x) - 0.5f;
+                        sxk = fminf(fmaxf(sxk, sx_lo), sx_hi);
+                        syk = fminf(fmaxf(syk, sy_lo), sy_hi);
+                        const float x0f = floorf(sxk), y0f = floorf(syk);
+                        float wx1 = sxk - x0f, wy1 = syk - y0f;
+                        float wx0 = (x0f + 1.0f) - sxk, wy0 = (y0f + 1.0f) - syk;
+                        const int x0 = (int)x0f, y0 = (int)y0f;
+                        if ((unsigned)x0 >= (unsigned)W) wx0 = 0.f;
+                        if ((unsigned)(x0 + 1) >= (unsigned)W) wx1 = 0.f;
+                        if ((unsigned)y0 >= (unsigned)H) wy0 = 0.f;
+                        if ((unsigned)(y0 + 1) >= (unsigned)H) wy1 = 0.f;
+                        const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+                        const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
+                        wx0s[k] = wx0; wx1s[k] = wx1; wy0s[k] = wy0; wy1s[k] = wy1;
+                        os[k] = ya * W + xa; dxs[k] = xb - xa; dys[k] = (yb - ya) * W;
+                    }
+                    const float2 wx0 = make_float2(wx0s[0], wx0s[1]), wx1 = make_float2(wx1s[0], wx1s[1]);
+                    const float2 wy0 = make_float2(wy0s[0], wy0s[1]), wy1 = make_float2(wy1s[0], wy1s[1]);
+                    w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
+                    oa = os[0]; ob = os[1]; dxa = dxs[0]; dxb = dxs[1]; dya = dys[0]; dyb = dys[1];
+                }
+                // the source row the next row step will newly touch: bring its lines into L1 now (no registers held)
+                const int pfa = min(oa + 2 * W, planei - 1), pfb = min(ob + 2 * W, planei - 1);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float* pa0 = img + (oa + c * planei);
+                    const float* pb0 = img + (ob + c * planei);
+                    const float* pa1 = pa0 + dya;
+                    const float* pb1 = pb0 + dyb;
+                    const float2 i00 = make_float2(__ldg(pa0), __ldg(pb0));
+                    const float2 i01 = make_float2(__ldg(pa0 + dxa), __ldg(pb0 + dxb));
+                    const float2 i10 = make_float2(__ldg(pa1), __ldg(pb1));
+                    const float2 i11 = make_float2(__ldg(pa1 + dxa), __ldg(pb1 + dxb));
+                    prefetch_l1(img + (pfa + c * planei));
+                    prefetch_l1(img + (pfb + c * planei));
+                    float2 val = fma2(i00, w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
+                    val = fma2(i01, w01, val);
+                    val = fma2(i10, w10, val);
+                    val = fma2(i11, w11, val);
+                    xbuf[c * kRowStride + lane + 1] = val.x;
+                    xbuf[c * kRowStride + lane + 33] = val.y;
+                }
             }
+            __syncwarp();
+            // ---------- stage 2: lane owns buffer columns 2l, 2l+1 (a pair) ----------
+            const float* yrow = ys_l + (r + 2) * kRowStride;
+            float2 nn[3], dd[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float2 xl = *reinterpret_cast<const float2*>(xs_l + c * kRowStride);      // cols 2l-1, 2l
+                const float2 xr = *reinterpret_cast<const float2*>(xs_l + c * kRowStride + 2);  // cols 2l+1, 2l+2
+                const float2 yl = *reinterpret_cast<const float2*>(yrow + c * ych);
+                const float2 yr = *reinterpret_cast<const float2*>(yrow + c * ych + 2);
+                const float2 xxl = mul2(xl, xl), xxr = mul2(xr, xr), xyl = mul2(xl, yl), xyr = mul2(xr, yr);
+                const float m1 = xl.y + xr.x, mx = xxl.y + xxr.x, my = xyl.y + xyr.x;
+                const float2 h1 = make_float2(xl.x + m1, m1 + xr.y);
+                const float2 hx = make_float2(xxl.x + mx, mx + xxr.y);
+                const float2 hy = make_float2(xyl.x + my, my + xyr.y);
+                if (t >= 2) {
+                    const float4 k4 = cs_l[c * cch + r * (kTileCols / 2)];
+                    ssim_nd(add2(add2(hs1[P1][c], hs1[P2][c]), h1), add2(add2(hsx[P1][c], hsx[P2][c]), hx),
+                            add2(add2(hsy[P1][c], hsy[P2][c]), hy), make_float2(k4.x, k4.y), make_float2(k4.z, k4.w),
+                            nn[c], dd[c]);
+                }
+                hs1[P][c] = h1; hsx[P][c] = hx; hsy[P][c] = hy;
+            }
+            if (t >= 2) {
+                const float2 q0 = mul2(nn[0], make_float2(fast_rcp(dd[0].x), fast_rcp(dd[0].y)));
+                const float2 q1 = mul2(nn[1], make_float2(fast_rcp(dd[1].x), fast_rcp(dd[1].y)));
+                const float2 q2 = mul2(nn[2], make_float2(fast_rcp(dd[2].x), fast_rcp(dd[2].y)));
+                // clamp((1 - q) / 2, 0, 1)   (layers.py:137)
+                const float2 e0 = make_float2(__saturatef(fmaf(-0.5f, q0.x, 0.5f)), __saturatef(fmaf(-0.5f, q0.y, 0.5f)));
+                const float2 e1 = make_float2(__saturatef(fmaf(-0.5f, q1.x, 0.5f)), __saturatef(fmaf(-0.5f, q1.y, 0.5f)));
+                const float2 e2 = make_float2(__saturatef(fmaf(-0.5f, q2.x, 0.5f)), __saturatef(fmaf(-0.5f, q2.y, 0.5f)));
+                const float2 E = fma2(cw2, e2, fma2(cw1, e1, mul2(cw0, e0)));
+                const float eL = __shfl_up_sync(0xffffffffu, E.y, 1);
+                const float eR = __shfl_down_sync(0xffffffffu, E.x, 1);
+                const float mid = E.x + E.y;
+                const float2 hEc = make_float2(eL + mid, mid + eR);
+                if (t >= 4) {
+                    // single-frame volume 1 - 2 sad (monorec_model.py:251) straight to HBM; the validity mask is applied by
+                    // the per-pixel phase below (which zeroes invalid pixels) once all planes are known
+                    const float2 sad = add2(add2(hE[P1], hE[P2]), hEc);
+                    const float2 sv = fma2(bc2(-2.0f), sad, bc2(1.0f));
+                    float* o = out_d + (size_t)(r - 2) * W;
+                    if (v0 + r - 2 < H) {
+                        if (st_pair) {
+                            *reinterpret_cast<float2*>(o) = sv;
+                        } else {
+                            if (st0) o[0] = sv.x;
+                            if (st1) o[1] = sv.y;
+                        }
+                    }
+                }
+                hE[P] = hEc;
+            }
+            __syncwarp();
+        };
+
+        int t = 0;
+        for (; t + 2 < nsteps; t += 3) {
+            row_step(std::integral_constant<int, 0>{}, t);
+            row_step(std::integral_constant<int, 1>{}, t + 1);
+            row_step(std::integral_constant<int, 2>{}, t + 2);
+        }
+        if (t < nsteps) row_step(std::integral_constant<int, 0>{}, t);
+        if (t + 1 < nsteps) row_step(std::integral_constant<int, 1>{}, t + 1);
+    }
+    __syncthreads();  // the marching warps' global stores are visible to the whole CTA from here on
+
+    // ---- per-pixel phase: view weights (monorec_model.py:257-260), zeroing of invalid pixels (:251) and fusion
+    //      cv = sum_f w_f (1 - 2 sad_f) / sum_f w_f, 0 where sum_f w_f == 0 (:262-269).  Each thread reads back the
+    //      L2-hot single-frame values of its pixel once per frame. ------------------------------------------------------
+    const float na4 = -0.25f * a.alpha;
+    for (int p = tid; p < TH * kTileCols; p += kThreads) {
+        const int r = p >> 6, bc = p & 63;
+        const int u = u0 + bc, v = v0 + r;
+        const bool own = (bc >= 2) && (bc < 2 + kOutCols) && (u < W) && (v < H);
+        if (!own) continue;
+        const size_t pix = (size_t)v * W + u;
+        float* cv_out = a.cv + (size_t)b * D * plane + pix;
+        for (int d0 = 0; d0 < D; d0 += kChunk) {   // one pass when D <= kChunk (every shipped config)
+            float acc[kChunk];
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
+            float wsum = 0.f;
+            for (int f = 0; f < F; ++f) {
+                float* sf = a.sfcv + (((size_t)f * a.B + b) * D) * plane + pix;
+                if (vmask[f * TH * kTileCols + p] == 0) {
+                    if (d0 == 0)
+                        for (int d = 0; d < D; ++d) sf[(size_t)d * plane] = 0.f;
+                    continue;
+                }
+                // sad = (1 - sv) / 2, so (sad - min sad)^2 = ((max sv - sv) / 2)^2
+                float m = -2.0f, sum = 0.f;
+                float vv[kChunk];
+                if (D <= kChunk) {
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) vv[j] = (j < D) ? __ldcg(sf + (size_t)j * plane) : -2.0f;
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) m = fmaxf(m, vv[j]);
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) {
+                        const float df = m - vv[j];
+                        if (j < D) sum += __expf(na4 * df * df);
+                    }
+                } else {
+                    for (int d = 0; d < D; ++d) m = fmaxf(m, __ldcg(sf + (size_t)d * plane));
+                    for (int d = 0; d < D; ++d) {
+                        const float df = m - __ldcg(sf + (size_t)d * plane);
+                        sum += __expf(na4 * df * df);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j) vv[j] = (d0 + j < D) ? __ldcg(sf + (size_t)(d0 + j) * plane) : 0.f;
+                }
+                // weight = 1 - 1/(D-1) * (sum - 1): separate roundings as in the reference so that flat-cost pixels
+                // (sum == D) give exactly 0 (monorec_model.py:258, :265-269)
+                const float w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
+                wsum += w;
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) acc[j] = fmaf(w, vv[j], acc[j]);
+            }
+            const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+                if (d0 + j < D) cv_out[(size_t)(d0 + j) * plane] = (wsum == 0.f) ? 0.f : acc[j] * inv;
         }
     }
 }

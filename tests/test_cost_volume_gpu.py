@@ -44,12 +44,31 @@ def test_golden_kitti_sample():
     H, W = ref_arg.shape[-2:]
     ref_zero = torch.from_numpy(np.unpackbits(g["cv_zero"])[: H * W].reshape(1, H, W).astype(bool))
     mine_zero = (cv == 0).all(1)
-    sel = (~ref_zero) & (~mine_zero) & (margin > 1e-4)
-    agree = (cv.argmax(1) == ref_arg)[sel].float().mean().item()
-    raw = (cv.argmax(1) == ref_arg)[(~ref_zero) & (~mine_zero)].float().mean().item()
+    # per-frame validity must agree too (a boundary pixel whose bilinear mask sample is +-0 flips valid_f, which changes
+    # the fused value completely; SURVEY.md §8c allows a few such pixels per frame and excludes them from the gate)
+    nF = len(sf)
+    ref_sf_zero = np.unpackbits(g["sf_zero"])[: nF * H * W].reshape(nF, 1, H, W).astype(bool)
+    masks_agree = torch.ones(1, H, W, dtype=torch.bool)
+    mask_flips = 0
+    for f in range(nF):
+        mz = (sf[f] == 0).all(1)
+        rz = torch.from_numpy(ref_sf_zero[f])
+        masks_agree &= (mz == rz)
+        mask_flips += int((mz != rz).sum())
+    assert mask_flips <= 4 * nF, f"{mask_flips} validity flips"
+    both = (~ref_zero) & (~mine_zero) & masks_agree
+    same = cv.argmax(1) == ref_arg
+    agree4 = same[both & (margin > 1e-4)].float().mean().item()
+    agree3 = same[both & (margin > 1e-3)].float().mean().item()
+    raw = same[both].float().mean().item()
     flips = int((ref_zero != mine_zero).sum())
-    print("kitti", stats, stats_rows, "argmax gated", agree, "raw", raw, "zero-set flips", flips)
-    assert agree == 1.0
+    print("kitti", stats, stats_rows, "argmax margin>1e-3", agree3, "margin>1e-4", agree4, "raw", raw,
+          "zero-set flips", flips, "validity flips", mask_flips)
+    # fp32 noise floor of the reference itself (fp32 vs fp64 run of the unmodified reference, make_golden.py):
+    # raw agreement 99.83 %, volume max|d| 8.9e-4.  Two volumes that agree to 1e-3 can only flip an argmax whose
+    # top1-top2 margin is below 2e-3, so the hard gate is margin > 1e-3; the 1e-4 band is reported and bounded.
+    assert agree3 == 1.0
+    assert agree4 > 0.9999
     assert raw > 0.997
     assert flips <= 600  # flat-cost pixels (exact-zero weights) sit on an fp32 knife edge: reference fp32 vs fp64 differ on 234
     # per-plane checksums of the full-resolution volume
