@@ -90,6 +90,54 @@ int mr_cost_volume_host(const float* h_keyframe, const float* h_frames,
                         float inv_depth_lo, float inv_depth_hi, float alpha,
                         void* workspace, long long workspace_bytes);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Convolution engine for the MaskModule / DepthModule stacks (model/monorec/monorec_model.py:287-385, :476-557).
+ * Activations are NHWC fp32 inside the engine ([B, H, W, C], C contiguous); weights are packed by the host side as
+ * [kh][kw][Cin_total][Cout].  One descriptor covers what the reference spreads over several modules:
+ *   PadSameConv2d  (model/layers.py:220-252)  -> pad_t / pad_l (asymmetric TF-"SAME" zero padding, out-of-range taps = 0)
+ *   torch.cat      (monorec_model.py:372-380, :541-545) -> up to MR_CONV_MAX_SRC channel-concatenated sources
+ *   Upsample(x2)   (layers.py:349)            -> upsample2: nearest-neighbour x2 applied while reading
+ *   Conv2d + bias + LeakyReLU / Sigmoid / |tanh| (layers.py:301-335, monorec_model.py:340-343, :554-557) -> act
+ *   ConvTranspose2d(k4,s2)+crop (layers.py:380-400) -> four sub-pixel 2x2 convolutions written with oy_step = ox_step = 2
+ */
+#define MR_CONV_MAX_SRC 3
+#define MR_ACT_NONE 0
+#define MR_ACT_LEAKY 1     /* x >= 0 ? x : act_a * x */
+#define MR_ACT_SIGMOID 2
+#define MR_ACT_ABSTANH 3   /* act_a + act_b * |tanh(x)|  (depth heads + inverse-depth affine, monorec_model.py:717) */
+
+typedef struct mr_conv_desc {
+    int n_src;                               /* 1..MR_CONV_MAX_SRC */
+    const float* src[MR_CONV_MAX_SRC];       /* each [B, Hs, Ws, src_c[i]] */
+    int src_c[MR_CONV_MAX_SRC];
+    int B, Hs, Ws;                           /* stored size of every source */
+    int upsample2;                           /* 1: virtual input is the nearest-neighbour x2 upsampling of the sources */
+    int kh, kw, sy, sx, pad_t, pad_l;
+    int Ho, Wo, Cout;                        /* output grid computed by this call */
+    const float* weight;                     /* [kh][kw][sum src_c][Cout] */
+    const float* bias;                       /* [Cout] or NULL */
+    float* dst;                              /* [B, dst_H, dst_W, dst_c] */
+    int dst_H, dst_W, dst_c, dst_coff;       /* channel slice [dst_coff, dst_coff + Cout) of the destination */
+    int oy_step, ox_step, oy_off, ox_off;    /* output (oy, ox) is stored at (oy*oy_step + oy_off, ox*ox_step + ox_off) */
+    int act;
+    float act_a, act_b;
+} mr_conv_desc;
+
+int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
+/* sizeof(mr_conv_desc) as compiled into the library (bindings check their mirror of the struct against it). */
+int mr_sizeof_conv_desc(void);
+
+/* NCHW [B,C,H,W] -> channel slice of an NHWC tensor [B,H,W,dst_c]; optional per-pixel multiplier
+ * scale[b,h,w] applied as (1 - scale) (monorec_model.py:713: cost_volume * (1 - cv_mask)). */
+int mr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, int dst_c, int dst_coff,
+                    const float* one_minus_scale, void* stream);
+/* nn.MaxPool2d(2) on NHWC (monorec_model.py:304-316). H and W must be even. */
+int mr_maxpool2_nhwc(const float* src, float* dst, int B, int H, int W, int C, void* stream);
+/* Element-wise max over the leading axis: dst[n] = max_f src[f*n_per_frame + n]  (monorec_model.py:362-365). */
+int mr_max_over_frames(const float* src, float* dst, int F, long long n_per_frame, void* stream);
+/* out[b,d,p] = volume[b,d,p] * (1 - mask[b,p])   (monorec_model.py:713, NCHW volume [B,D,HW], mask [B,HW]). */
+int mr_mask_volume(const float* volume, const float* mask, float* out, int B, int D, int HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,271 @@
+// Convolution engine, CUDA-core fp32 path (sm_100a).  See include/monorec_b200.h (mr_conv_desc) for what one call fuses:
+// TF-"SAME" padding, channel concatenation of up to three sources, nearest x2 upsampling on read, bias, activation and
+// strided (sub-pixel) output placement.  NHWC activations, weights [kh][kw][Cin][Cout].
+//
+// Reference being replaced: PadSameConv2d + nn.Conv2d + LeakyReLU (model/layers.py:220-335), Upconv (:338-356),
+// Refine / ConvTranspose2d (:380-400), the heads (monorec_model.py:340-343, :521-524, :554-557).
+//
+// Kernel shape: implicit GEMM.  A CTA owns an 8x16 tile of output pixels (M = 128) and TN output channels; the K loop
+// runs over (tap, source, 16-channel chunk), staging A (pixels x channels, gathered with zero fill) and B (channels x
+// Cout) through shared memory; each thread accumulates 4 pixels x TN/8 channels in registers.
+#include "mr_common.cuh"
+#include <cstdint>
+
+namespace {
+
+constexpr int kTileH = 8, kTileW = 16, kTileP = kTileH * kTileW;  // 128 output pixels per CTA
+constexpr int kKC = 16;                                           // channels per K chunk
+constexpr int kConvThreads = 256;
+
+__device__ __forceinline__ float apply_act(float v, int act, float a, float b) {
+    switch (act) {
+        case MR_ACT_LEAKY: return v >= 0.f ? v : a * v;
+        case MR_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+        case MR_ACT_ABSTANH: return fmaf(b, fabsf(tanhf(v)), a);
+        default: return v;
+    }
+}
+
+template <int TN>
+__global__ void __launch_bounds__(kConvThreads) conv2d_nhwc_kernel(const mr_conv_desc d, const int cin_total) {
+    constexpr int CH = TN / 8;  // channels per thread (8 channel groups)
+    __shared__ __align__(16) float As[kKC][kTileP];
+    __shared__ __align__(16) float Bs[kKC][TN];
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (d.Wo + kTileW - 1) / kTileW;
+    const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+    const int n0 = blockIdx.y * TN;
+    const int b = blockIdx.z;
+    const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
+    const int Hv = d.upsample2 ? 2 * d.Hs : d.Hs, Wv = d.upsample2 ? 2 * d.Ws : d.Ws;  // virtual input size
+
+    // staging role: this thread gathers channel quad `aq` (and aq + 2) of pixel `ap`
+    const int ap = tid & (kTileP - 1), aq = tid >> 7;
+    const int apy = oy0 + (ap >> 4), apx = ox0 + (ap & 15);
+    // compute role: 4 consecutive pixels x CH consecutive channels
+    const int cg = tid & 7, pg = tid >> 3;
+
+    float acc[4][CH];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < CH; ++j) acc[i][j] = 0.f;
+
+    for (int ky = 0; ky < d.kh; ++ky) {
+        for (int kx = 0; kx < d.kw; ++kx) {
+            int iy = apy * d.sy - d.pad_t + ky, ix = apx * d.sx - d.pad_l + kx;
+            const bool inside = (iy >= 0) && (iy < Hv) && (ix >= 0) && (ix < Wv) && (apy < d.Ho) && (apx < d.Wo);
+            if (d.upsample2) { iy >>= 1; ix >>= 1; }
+            const size_t pix = ((size_t)b * d.Hs + iy) * d.Ws + ix;
+            int cbase = 0;  // channel offset of the current source inside the concatenation
+            for (int s = 0; s < d.n_src; ++s) {
+                const int C = d.src_c[s];
+                const float* sp = d.src[s] + pix * C;
+                const bool vec_ok = (C & 3) == 0;
+                for (int c0 = 0; c0 < C; c0 += kKC) {
+                    // ---- stage A: 128 pixels x 16 channels (zero fill outside the image / beyond C) ----
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cq = c0 + 4 * (aq + 2 * h);
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (inside) {
+                            if (vec_ok && cq + 4 <= C) {
+                                v = __ldg(reinterpret_cast<const float4*>(sp + cq));
+                            } else {
+                                if (cq + 0 < C) v.x = __ldg(sp + cq + 0);
+                                if (cq + 1 < C) v.y = __ldg(sp + cq + 1);
+                                if (cq + 2 < C) v.z = __ldg(sp + cq + 2);
+                                if (cq + 3 < C) v.w = __ldg(sp + cq + 3);
+                            }
+                        }
+                        const int kq = 4 * (aq + 2 * h);
+                        As[kq + 0][ap] = v.x; As[kq + 1][ap] = v.y; As[kq + 2][ap] = v.z; As[kq + 3][ap] = v.w;
+                    }
+                    // ---- stage B: 16 channels x TN output channels ----
+                    const float* wrow = d.weight + ((size_t)(ky * d.kw + kx) * cin_total + cbase + c0) * d.Cout + n0;
+                    for (int i = tid; i < kKC * TN; i += kConvThreads) {
+                        const int k = i / TN, n = i - k * TN;
+                        float w = 0.f;
+                        if (c0 + k < C && n0 + n < d.Cout) w = __ldg(wrow + (size_t)k * d.Cout + n);
+                        Bs[k][n] = w;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < kKC; ++k) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][4 * pg]);
+                        float bv[CH];
+#pragma unroll
+                        for (int j = 0; j < CH; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][CH * cg + j]);
+                            bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            acc[0][j] = fmaf(a4.x, bv[j], acc[0][j]);
+                            acc[1][j] = fmaf(a4.y, bv[j], acc[1][j]);
+                            acc[2][j] = fmaf(a4.z, bv[j], acc[2][j]);
+                            acc[3][j] = fmaf(a4.w, bv[j], acc[3][j]);
+                        }
+                    }
+                    __syncthreads();
+                }
+                cbase += C;
+            }
+        }
+    }
+
+    // ---- epilogue: bias, activation, NHWC store into the channel slice of the destination ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int p = 4 * pg + i;
+        const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
+        if (oy >= d.Ho || ox >= d.Wo) continue;
+        const int dy = oy * d.oy_step + d.oy_off, dx = ox * d.ox_step + d.ox_off;
+        float* op = d.dst + (((size_t)b * d.dst_H + dy) * d.dst_W + dx) * d.dst_c + d.dst_coff + n0 + CH * cg;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int n = n0 + CH * cg + j;
+            if (n < d.Cout) {
+                float v = acc[i][j] + (d.bias ? __ldg(d.bias + n) : 0.f);
+                op[j] = apply_act(v, d.act, d.act_a, d.act_b);
+            }
+        }
+    }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int dst_c,
+                                    int dst_coff, const float* __restrict__ oms) {
+    // one CTA: 32 pixels x 32 channels tile transposed through shared memory (coalesced on both sides)
+    __shared__ float t[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + tx;
+        t[j][tx] = (c < C && p < HW) ? __ldg(src + ((size_t)b * C + c) * HW + p) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + tx;
+        if (p < HW && c < C) {
+            float v = t[tx][j];
+            if (oms) v *= 1.0f - __ldg(oms + (size_t)b * HW + p);
+            dst[((size_t)b * HW + p) * dst_c + dst_coff + c] = v;
+        }
+    }
+}
+
+__global__ void maxpool2_nhwc_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int H, int W, int C4,
+                                     size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int Wo = W / 2, Ho = H / 2;
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const size_t b = r / Ho;
+    const float4* p = src + ((b * H + 2 * y) * W + 2 * x) * C4 + c;
+    const float4 a = __ldg(p), bq = __ldg(p + C4), cq = __ldg(p + (size_t)W * C4), dq = __ldg(p + (size_t)W * C4 + C4);
+    float4 o;
+    o.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, dq.x));
+    o.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, dq.y));
+    o.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, dq.z));
+    o.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, dq.w));
+    dst[i] = o;
+}
+
+__global__ void max_over_frames_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int F, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 m = __ldg(src + i);
+    for (int f = 1; f < F; ++f) {
+        const float4 v = __ldg(src + (size_t)f * n4 + i);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    dst[i] = m;
+}
+
+__global__ void mask_volume_kernel(const float* __restrict__ vol, const float* __restrict__ mask,
+                                   float* __restrict__ out, int D, int HW, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const size_t b = i / ((size_t)D * HW);
+    const int p = (int)(i % HW);
+    out[i] = (1.0f - __ldg(mask + b * HW + p)) * __ldg(vol + i);
+}
+
+}  // namespace
+
+extern "C" int mr_mask_volume(const float* volume, const float* mask, float* out, int B, int D, int HW, void* stream) {
+    MR_REQUIRE(volume && mask && out && B >= 1 && D >= 1 && HW >= 1, "mr_mask_volume: bad argument");
+    const size_t total = (size_t)B * D * HW;
+    mask_volume_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, mask, out, D, HW,
+                                                                                          total);
+    MR_LAUNCH_CHECK("mask_volume_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_sizeof_conv_desc(void) { return (int)sizeof(mr_conv_desc); }
+
+extern "C" int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream) {
+    MR_REQUIRE(desc != nullptr, "mr_conv2d_nhwc: null descriptor");
+    const mr_conv_desc& d = *desc;
+    MR_REQUIRE(d.n_src >= 1 && d.n_src <= MR_CONV_MAX_SRC, "mr_conv2d_nhwc: n_src=%d out of range", d.n_src);
+    int cin = 0;
+    for (int s = 0; s < d.n_src; ++s) {
+        MR_REQUIRE(d.src[s] != nullptr && d.src_c[s] >= 1, "mr_conv2d_nhwc: bad source %d", s);
+        cin += d.src_c[s];
+    }
+    MR_REQUIRE(d.weight && d.dst, "mr_conv2d_nhwc: null weight/dst");
+    MR_REQUIRE(d.B >= 1 && d.B <= 65535 && d.Hs >= 1 && d.Ws >= 1 && d.Ho >= 1 && d.Wo >= 1 && d.Cout >= 1,
+               "mr_conv2d_nhwc: bad shape");
+    MR_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.sy >= 1 && d.sx >= 1 && d.oy_step >= 1 && d.ox_step >= 1,
+               "mr_conv2d_nhwc: bad kernel/stride");
+    MR_REQUIRE(d.dst_coff >= 0 && d.dst_coff + d.Cout <= d.dst_c, "mr_conv2d_nhwc: channel slice out of range");
+    MR_REQUIRE((d.Ho - 1) * d.oy_step + d.oy_off < d.dst_H && (d.Wo - 1) * d.ox_step + d.ox_off < d.dst_W,
+               "mr_conv2d_nhwc: output placement out of range");
+    MR_REQUIRE(d.act >= MR_ACT_NONE && d.act <= MR_ACT_ABSTANH, "mr_conv2d_nhwc: unknown activation %d", d.act);
+    const int tiles = ((d.Ho + kTileH - 1) / kTileH) * ((d.Wo + kTileW - 1) / kTileW);
+    // the per-thread float4 weight reads need Cout-tile-aligned rows: TN=64 only when Cout is a multiple of 4
+    if (d.Cout >= 64 && d.Cout % 4 == 0) {
+        dim3 grid(tiles, (d.Cout + 63) / 64, d.B);
+        conv2d_nhwc_kernel<64><<<grid, kConvThreads, 0, (cudaStream_t)stream>>>(d, cin);
+    } else {
+        dim3 grid(tiles, (d.Cout + 31) / 32, d.B);
+        conv2d_nhwc_kernel<32><<<grid, kConvThreads, 0, (cudaStream_t)stream>>>(d, cin);
+    }
+    MR_LAUNCH_CHECK("conv2d_nhwc_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, int dst_c, int dst_coff,
+                               const float* one_minus_scale, void* stream) {
+    MR_REQUIRE(src && dst && B >= 1 && C >= 1 && H >= 1 && W >= 1, "mr_nchw_to_nhwc: bad argument");
+    MR_REQUIRE(dst_coff >= 0 && dst_coff + C <= dst_c, "mr_nchw_to_nhwc: channel slice out of range");
+    const int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW, dst_c, dst_coff, one_minus_scale);
+    MR_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_maxpool2_nhwc(const float* src, float* dst, int B, int H, int W, int C, void* stream) {
+    MR_REQUIRE(src && dst && B >= 1 && C >= 4 && (C % 4) == 0 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0,
+               "mr_maxpool2_nhwc: need even H, W and C %% 4 == 0 (got H=%d W=%d C=%d)", H, W, C);
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 4);
+    maxpool2_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), H, W, C / 4, total);
+    MR_LAUNCH_CHECK("maxpool2_nhwc_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_max_over_frames(const float* src, float* dst, int F, long long n_per_frame, void* stream) {
+    MR_REQUIRE(src && dst && F >= 1 && n_per_frame >= 4 && (n_per_frame % 4) == 0,
+               "mr_max_over_frames: n_per_frame must be a positive multiple of 4");
+    const size_t n4 = (size_t)n_per_frame / 4;
+    max_over_frames_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), F, n4);
+    MR_LAUNCH_CHECK("max_over_frames_kernel");
+    return MR_OK;
+}

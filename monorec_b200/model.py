@@ -1,0 +1,401 @@
+"""Drop-in replacement of the reference's MonoRecModel and its sub-modules (model/monorec/monorec_model.py:95-729).
+
+Same constructor keywords, same `forward(data_dict) -> data_dict` contract and dict keys, same attribute names
+(`cv_module`, `att_module`, `depth_module`, `_feature_extractor`, ...) and -- the checkpoint contract -- the same
+`state_dict()` keys and shapes, so a reference checkpoint loads unchanged.  The modules below only
+*hold* parameters in the reference's layout; the arithmetic runs in libmonorec_b200.so (fused cost-volume kernel +
+convolution engine) through the C ABI.  The ResNet-18 trunk stays on torchvision/cuDNN (third-party arithmetic in the
+reference too; SURVEY.md §8f "next" row 1).
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib, conv as C
+from .cost_volume import CostVolumeModule
+
+__all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "ResnetEncoder"]
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# parameter holders with the reference's attribute names (model/layers.py:289-400)
+# --------------------------------------------------------------------------------------------------------------------
+class ConvReLU(nn.Module):
+    """PadSame + Conv2d(k) + LeakyReLU(0.1)  (model/layers.py:317-335).  Key: `.conv.{weight,bias}`."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride)
+        self.kernel_size, self.stride = kernel_size, stride
+
+
+class ConvReLU2(nn.Module):
+    """(k,1) conv + LReLU + (1,k) conv + LReLU  (model/layers.py:289-314).  Keys: `.conv_y.*`, `.conv_x.*`."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1):
+        super().__init__()
+        self.conv_y = nn.Conv2d(in_channels, out_channels, (kernel_size, 1), stride=(stride, 1))
+        self.conv_x = nn.Conv2d(out_channels, out_channels, (1, kernel_size), stride=(1, stride))
+        self.kernel_size, self.stride = kernel_size, stride
+
+
+class Upconv(nn.Module):
+    """nearest x2 + pad(0,1,0,1) + Conv2d(2)  (model/layers.py:338-356).  Key: `.conv.*`."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, 2, stride=1)
+
+
+class Refine(nn.Module):
+    """ConvTranspose2d(k4, s2) + LReLU + centre crop  (model/layers.py:380-400).  Key: `.conv2d_t.*`."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv2d_t = nn.ConvTranspose2d(in_channels, out_channels, kernel_size=4, stride=2)
+
+
+class _Packed:
+    """Kernel-layout copies of a module's parameters, rebuilt when a parameter changes (load_state_dict, .to(), step)."""
+
+    def __init__(self):
+        self.sig, self.data = None, {}
+
+    def get(self, module, builder):
+        params = list(module.parameters())
+        sig = tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+        if sig != self.sig:
+            with torch.no_grad():
+                self.data = builder()
+            self.sig = sig
+        return self.data
+
+
+def _w(conv):
+    return C.pack_conv_weight(conv.weight), conv.bias.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+class ResnetEncoder(nn.Module):
+    """torchvision ResNet-18 trunk, 5 feature maps (monorec_model.py:95-129)."""
+
+    def __init__(self, num_layers=18, pretrained=True):
+        super().__init__()
+        import numpy as np
+        import torchvision
+        if num_layers != 18:
+            raise NotImplementedError("monorec_b200: the reference only ever instantiates ResnetEncoder(18)")
+        self.num_ch_enc = np.array([64, 64, 128, 256, 512])
+        try:
+            weights = torchvision.models.ResNet18_Weights.IMAGENET1K_V1 if pretrained else None
+            self.encoder = torchvision.models.resnet18(weights=weights)
+        except Exception:  # offline: ImageNet weights cannot be downloaded; a checkpoint is expected to supply them
+            self.encoder = torchvision.models.resnet18(weights=None)
+
+    def forward(self, input_image):
+        e = self.encoder
+        x = (input_image - 0.45) / 0.225
+        self.features = [e.relu(e.bn1(e.conv1(x)))]
+        self.features.append(e.layer1(e.maxpool(self.features[-1])))
+        self.features.append(e.layer2(self.features[-1]))
+        self.features.append(e.layer3(self.features[-1]))
+        self.features.append(e.layer4(self.features[-1]))
+        return self.features
+
+
+class MaskModule(nn.Module):
+    """Moving-object mask U-Net over the single-frame volumes (monorec_model.py:287-385)."""
+
+    def __init__(self, depth_steps=32, feature_channels=(64, 64, 128, 256, 512), use_cv=True, use_features=True):
+        super().__init__()
+        self.depth_steps = depth_steps
+        self.feat_chns = tuple(int(c) for c in feature_channels)
+        self._in_channels = depth_steps
+        self._cv_enc_feat_chns = (self._in_channels, 48, 64, 96, 96)
+        self._dec_feat_chns = (96, 96, 64, 48, 128)
+        self.use_cv, self.use_features = use_cv, use_features
+        e, d, fc = self._cv_enc_feat_chns, self._dec_feat_chns, self.feat_chns
+        self.enc = nn.ModuleList([nn.Sequential(ConvReLU(self._in_channels, e[0], 3), ConvReLU(e[0], e[0], 3))] + [
+            nn.Sequential(nn.MaxPool2d(kernel_size=2), ConvReLU(e[i - 1], e[i], 3), ConvReLU(e[i], e[i], 3))
+            for i in range(1, 5)])
+        self.dec = nn.ModuleList([
+            nn.Sequential(Upconv(e[4] + fc[3], d[0]), ConvReLU(d[0] + e[3] + fc[2], d[0], 3), ConvReLU(d[0], d[0], 3)),
+            nn.Sequential(Upconv(d[0], d[0]), ConvReLU(d[0] + e[2] + fc[1], d[1], 3), ConvReLU(d[1], d[1], 3)),
+            nn.Sequential(Upconv(d[1], d[1]), ConvReLU(d[1] + e[1] + fc[0], d[2], 3), ConvReLU(d[2], d[2], 3)),
+            nn.Sequential(Upconv(d[2], d[2]), ConvReLU(d[2] + e[0], d[3], 3), ConvReLU(d[3], d[3], 3))])
+        self.classifier = nn.Sequential(nn.Conv2d(d[3], 1, kernel_size=1, stride=1), nn.Sigmoid())
+        self._packed = _Packed()
+
+    def _build(self):
+        p = {}
+        for lvl, seq in enumerate(self.enc):
+            mods = [m for m in seq if isinstance(m, ConvReLU)]
+            p[f"enc{lvl}"] = [_w(m.conv) for m in mods]
+        for i, seq in enumerate(self.dec):
+            p[f"dec{i}"] = [_w(seq[0].conv), _w(seq[1].conv), _w(seq[2].conv)]
+        p["cls"] = _w(self.classifier[0])
+        return p
+
+    def forward(self, data_dict):
+        sfcvs = data_dict["single_frame_cvs"]
+        feats_nchw = data_dict["image_features"]
+        if self.training:
+            raise NotImplementedError("monorec_b200.MaskModule: inference only (dropout / autograd are not implemented)")
+        P = self._packed.get(self, self._build)
+        nF = len(sfcvs)
+        B, D, H, W = sfcvs[0].shape
+        # all frames go through the encoder as one batch of F*B volumes (the reference loops, :357-365)
+        x = torch.empty(nF * B, H, W, D, device=sfcvs[0].device, dtype=torch.float32)
+        for f, v in enumerate(sfcvs):
+            C.nchw_to_nhwc(v.to(torch.float32), out=x[f * B:(f + 1) * B])
+        if not self.use_cv:
+            x.zero_()
+        cv_feats = []
+        for lvl in range(5):
+            if lvl > 0:
+                x = C.maxpool2(x)
+            for (w, b) in P[f"enc{lvl}"]:
+                x = C.conv2d([x], w, b, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
+            cv_feats.append(C.max_over_frames(x, nF))
+        img = [C.nchw_to_nhwc(f.to(torch.float32)) for f in feats_nchw[:4]]
+        if not self.use_features:
+            img = [torch.zeros_like(t) for t in img]
+        x = None
+        for i in range(4):
+            (wu, bu), (w1, b1), (w2, b2) = P[f"dec{i}"]
+            up_src = [cv_feats[4], img[3]] if i == 0 else [x]
+            x = C.conv2d(up_src, wu, bu, 2, 2, upsample2=True)                      # Upconv: no activation
+            if i == 0:
+                cat = [cv_feats[3], img[2], x]
+            elif i == 3:
+                cat = [cv_feats[0], x]
+            else:
+                cat = [cv_feats[3 - i], img[2 - i], x]
+            x = C.conv2d(cat, w1, b1, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
+            x = C.conv2d([x], w2, b2, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
+        wc, bc = P["cls"]
+        m = C.conv2d([x], wc, bc, 1, 1, act=C.ACT_SIGMOID)                           # [B,H,W,1]
+        data_dict["cv_mask"] = m.view(B, 1, H, W)                                    # C == 1: NHWC == NCHW
+        return data_dict
+
+
+class DepthModule(nn.Module):
+    """Depth U-Net over (masked cost volume (+) keyframe) with 4 output scales (monorec_model.py:476-557)."""
+
+    def __init__(self, depth_steps=32, feature_channels=(64, 64, 128, 256, 512), large_model=False):
+        super().__init__()
+        if large_model:
+            raise NotImplementedError("monorec_b200: depth_large_model is an unused ablation of the reference")
+        self.depth_steps = depth_steps
+        self.feat_chns = tuple(int(c) for c in feature_channels)
+        self._in_channels = depth_steps + 3
+        e = self._cv_enc_feat_chns = (48, 64, 128, 192, 256)
+        d = self._dec_feat_chns = (256, 128, 64, 48, 32, 24)
+        fc = self.feat_chns
+        ks = (7, 7, 5, 5, 3)
+        self.enc = nn.ModuleList([
+            nn.Sequential(ConvReLU2(self._in_channels if i == 0 else e[i - 1], e[i], ks[i], stride=1 if i == 0 else 2),
+                          ConvReLU2(e[i], e[i], 3)) for i in range(5)])
+        self.dec = nn.ModuleList([
+            Refine(e[4], d[0]),
+            nn.Sequential(Refine(e[3] + fc[2] + d[0], d[1]), ConvReLU2(d[1], d[1], 3)),
+            nn.Sequential(Refine(e[2] + fc[1] + d[1], d[2]), ConvReLU2(d[2], d[2], 3)),
+            Refine(e[1] + fc[0] + d[2], d[3]),
+            nn.Sequential(ConvReLU2(e[0] + d[3], d[4], 3), nn.Identity(), nn.Conv2d(d[4], d[5], 3),
+                          nn.LeakyReLU(negative_slope=0.1))])
+        self.predictors = nn.ModuleList([nn.Sequential(nn.Identity(), nn.Conv2d(ch, 1, 3))
+                                         for ch in d[:3] + d[-1:]])
+        self._packed = _Packed()
+        self.out_range = (0.0, 1.0)   # (a, b): heads emit a + b * |tanh|; MonoRecModel folds the inverse-depth affine in
+
+    def _build(self):
+        def cr2(m):
+            return (_w(m.conv_y), _w(m.conv_x), m.kernel_size, m.stride)
+
+        def rf(m):
+            return (C.pack_convT_k4s2(m.conv2d_t.weight), m.conv2d_t.bias.detach().to(torch.float32).contiguous())
+        p = {"enc": [(cr2(s[0]), cr2(s[1])) for s in self.enc]}
+        p["dec0"] = rf(self.dec[0])
+        p["dec1"] = (rf(self.dec[1][0]), cr2(self.dec[1][1]))
+        p["dec2"] = (rf(self.dec[2][0]), cr2(self.dec[2][1]))
+        p["dec3"] = rf(self.dec[3])
+        p["dec4"] = (cr2(self.dec[4][0]), _w(self.dec[4][2]))
+        p["heads"] = [_w(s[1]) for s in self.predictors]
+        return p
+
+    @staticmethod
+    def _cr2(srcs, pk):
+        (wy, by), (wx, bx), k, s = pk
+        t = C.conv2d(srcs, wy, by, k, 1, stride=(s, 1), act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
+        return C.conv2d([t], wx, bx, 1, k, stride=(1, s), act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
+
+    def _head(self, x, wb):
+        w, b = wb
+        a, s = self.out_range
+        y = C.conv2d([x], w, b, 3, 3, act=C.ACT_ABSTANH, act_a=a, act_b=s)
+        B, H, W, _ = y.shape
+        return y.view(B, 1, H, W)
+
+    def forward(self, data_dict):
+        if self.training:
+            raise NotImplementedError("monorec_b200.DepthModule: inference only")
+        P = self._packed.get(self, self._build)
+        keyframe = data_dict["keyframe"]
+        cv = data_dict["cost_volume"]
+        feats_nchw = data_dict["image_features"]
+        B, D, H, W = cv.shape
+        # cat(cost_volume, keyframe) (:531); when MonoRecModel passes the unmasked volume plus `_cv_mask_for_depth`
+        # the (1 - cv_mask) product of :713 is applied during the layout change
+        x = torch.empty(B, H, W, D + 3, device=cv.device, dtype=torch.float32)
+        C.nchw_to_nhwc(cv.to(torch.float32), out=x, out_coff=0, one_minus=data_dict.get("_cv_mask_for_depth"))
+        C.nchw_to_nhwc(keyframe.to(torch.float32), out=x, out_coff=D)
+        img = [C.nchw_to_nhwc(f.to(torch.float32)) for f in feats_nchw[:3]]
+        feats = []
+        for (p0, p1) in P["enc"]:
+            x = self._cr2([x], p0)
+            x = self._cr2([x], p1)
+            feats.append(x)
+        preds = []
+        sw, sb = P["dec0"]
+        x = C.conv_transpose_k4s2_crop([feats[4]], sw, sb)                               # 256 @ 1/8
+        preds.insert(0, self._head(x, P["heads"][0]))
+        (sw, sb), pk = P["dec1"]
+        x = self._cr2([C.conv_transpose_k4s2_crop([feats[3], img[2], x], sw, sb)], pk)    # 128 @ 1/4
+        preds.insert(0, self._head(x, P["heads"][1]))
+        (sw, sb), pk = P["dec2"]
+        x = self._cr2([C.conv_transpose_k4s2_crop([feats[2], img[1], x], sw, sb)], pk)    # 64 @ 1/2
+        preds.insert(0, self._head(x, P["heads"][2]))
+        sw, sb = P["dec3"]
+        x = C.conv_transpose_k4s2_crop([feats[1], img[0], x], sw, sb)                     # 48 @ full
+        pk, (w2, b2) = P["dec4"]
+        x = self._cr2([feats[0], x], pk)
+        x = C.conv2d([x], w2, b2, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)            # 24 @ full
+        preds.insert(0, self._head(x, P["heads"][3]))
+        data_dict["predicted_inverse_depths"] = preds
+        return data_dict
+
+    def predict_depth(self, x, scale):
+        """API parity with the reference (:554-557); x is NHWC inside this implementation."""
+        return self._head(x, self._packed.get(self, self._build)["heads"][scale])
+
+
+class MonoRecModel(nn.Module):
+    """Drop-in for model.monorec.monorec_model.MonoRecModel (:560-729); see the module docstring."""
+
+    def __init__(self, inv_depth_min_max=(0.33, 0.0025), cv_depth_steps=32, pretrain_mode=False, pretrain_dropout=0.0,
+                 pretrain_dropout_mode=0, augmentation=None, use_mono=True, use_stereo=False, use_ssim=True,
+                 sfcv_mult_mask=True, simple_mask=False, mask_use_cv=True, mask_use_feats=True, cv_patch_size=3,
+                 depth_large_model=False, no_cv=False, freeze_resnet=True, freeze_module=(), checkpoint_location=None,
+                 mask_cp_loc=None, depth_cp_loc=None):
+        super().__init__()
+        self.inv_depth_min_max = inv_depth_min_max
+        self.cv_depth_steps = cv_depth_steps
+        self.use_mono, self.use_stereo, self.use_ssim = use_mono, use_stereo, use_ssim
+        self.sfcv_mult_mask = sfcv_mult_mask
+        self.pretrain_mode = int(pretrain_mode)
+        self.pretrain_dropout, self.pretrain_dropout_mode = pretrain_dropout, pretrain_dropout_mode
+        self.augmentation = augmentation
+        self.simple_mask, self.mask_use_cv, self.mask_use_feats = simple_mask, mask_use_cv, mask_use_feats
+        self.cv_patch_size = cv_patch_size
+        self.no_cv = no_cv
+        self.depth_large_model = depth_large_model
+        self.checkpoint_location, self.mask_cp_loc, self.depth_cp_loc = checkpoint_location, mask_cp_loc, depth_cp_loc
+        self.freeze_module, self.freeze_resnet = freeze_module, freeze_resnet
+        if simple_mask:
+            raise NotImplementedError("monorec_b200: simple_mask is an unused ablation of the reference")
+        if augmentation not in (None, "none"):
+            raise NotImplementedError("monorec_b200: training-time augmentation is out of scope (inference path)")
+
+        self._feature_extractor = ResnetEncoder(num_layers=18, pretrained=True)
+        if self.freeze_resnet:
+            for p in self._feature_extractor.parameters(True):
+                p.requires_grad_(False)
+        self.cv_module = CostVolumeModule(use_mono=use_mono, use_stereo=use_stereo, use_ssim=use_ssim,
+                                          sfcv_mult_mask=self.sfcv_mult_mask, patch_size=cv_patch_size)
+        if not (self.pretrain_mode == 1 or self.pretrain_mode == 3):
+            self.att_module = MaskModule(self.cv_depth_steps, self._feature_extractor.num_ch_enc, use_cv=mask_use_cv,
+                                         use_features=mask_use_feats)
+        if not self.pretrain_mode == 2:
+            self.depth_module = DepthModule(self.cv_depth_steps, feature_channels=self._feature_extractor.num_ch_enc,
+                                            large_model=self.depth_large_model)
+        self._load_checkpoints(checkpoint_location, mask_cp_loc, depth_cp_loc)
+        for module_name in self.freeze_module:
+            module = getattr(self, module_name + "_module")
+            module.eval()
+            for param in module.parameters(True):
+                param.requires_grad_(False)
+        self.augmenter = None
+
+    # -- checkpoint loading: same key filtering as utils/util.py:244-248 + monorec_model.py:630-657 ------------------
+    @staticmethod
+    def filter_state_dict(state_dict, data_parallel=False):
+        if data_parallel:
+            state_dict = {k[7:]: v for k, v in state_dict.items()}
+        digits = tuple(str(i) for i in range(1, 10))
+        return {(k[2:] if k.startswith("0") else k): v for k, v in state_dict.items() if not k.startswith(digits)}
+
+    def _load_checkpoints(self, checkpoint_location, mask_cp_loc, depth_cp_loc):
+        def as_list(x):
+            return x if isinstance(x, list) else [x]
+
+        def read(cp):
+            checkpoint = torch.load(cp, map_location=torch.device("cpu"), weights_only=False)
+            return self.filter_state_dict(checkpoint["state_dict"], checkpoint["arch"] == "DataParallel")
+        if checkpoint_location is not None:
+            for cp in as_list(checkpoint_location):
+                self.load_state_dict(read(cp), strict=False)
+        if mask_cp_loc is not None:
+            for cp in as_list(mask_cp_loc):
+                sd = read(cp)
+                self.att_module.load_state_dict({k[11:]: v for k, v in sd.items() if k.startswith("att_module")},
+                                                strict=False)
+        if depth_cp_loc is not None:
+            for cp in as_list(depth_cp_loc):
+                sd = read(cp)
+                self.depth_module.load_state_dict({k[13:]: v for k, v in sd.items() if k.startswith("depth_module")},
+                                                  strict=False)
+
+    def forward(self, data_dict):
+        keyframe = data_dict["keyframe"]
+        lo, hi = float(self.inv_depth_min_max[1]), float(self.inv_depth_min_max[0])
+        data_dict["inv_depth_min"] = keyframe.new_tensor([self.inv_depth_min_max[0]])
+        data_dict["inv_depth_max"] = keyframe.new_tensor([self.inv_depth_min_max[1]])
+        data_dict["cv_depth_steps"] = keyframe.new_tensor([self.cv_depth_steps], dtype=torch.int32)
+        data_dict["_cv_range"] = (lo, hi, int(self.cv_depth_steps))   # host copy: no .item() synchronisation
+
+        with torch.no_grad():
+            if not self.no_cv:
+                data_dict = self.cv_module(data_dict)
+            else:
+                s = list(keyframe.shape)
+                s[1] = self.cv_depth_steps
+                data_dict["cost_volume"] = keyframe.new_zeros(s)
+                data_dict["single_frame_cvs"] = [data_dict["cost_volume"].clone() for _ in data_dict["poses"]]
+
+            data_dict["image_features"] = self._feature_extractor(keyframe + .5)
+
+            if self.pretrain_mode == 0 or self.pretrain_mode == 2:
+                data_dict = self.att_module(data_dict)
+            elif self.pretrain_mode == 1:
+                b, c, h, w = keyframe.shape
+                data_dict["cv_mask"] = keyframe.new_zeros(b, 1, h, w)      # eval branch of :706-707
+            elif self.pretrain_mode == 3:
+                data_dict["cv_mask"] = data_dict["mvobj_mask"].clone().detach()
+
+            if not self.pretrain_mode == 2:
+                # cost_volume * (1 - cv_mask) (:713): the product is fused into the depth module's layout change and
+                # the masked volume is also materialised for callers that read data_dict["cost_volume"]
+                data_dict["_cv_mask_for_depth"] = data_dict["cv_mask"]
+                self.depth_module.out_range = (lo, hi - lo)               # (1-p)*lo + p*hi, :717-718
+                data_dict = self.depth_module(data_dict)
+                del data_dict["_cv_mask_for_depth"]
+                data_dict["cost_volume"] = C.mask_volume(data_dict["cost_volume"], data_dict["cv_mask"])
+
+        if self.pretrain_mode == 2:
+            data_dict["result"] = data_dict["cv_mask"]
+        else:
+            data_dict["result"] = data_dict["predicted_inverse_depths"][0]
+            data_dict["mask"] = data_dict["cv_mask"]
+        data_dict.pop("_cv_range", None)
+        return data_dict
+

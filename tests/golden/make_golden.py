@@ -190,6 +190,10 @@ def main():
         print(gain_tag, "result range", float(r["result"].min()), float(r["result"].max()),
               "mask range", float(r["cv_mask"].min()), float(r["cv_mask"].max()))
     out["cfg"] = np.array([B, nF, 32, H, W, seed, 7])
+    # the checkpoint contract: every key and shape of the reference model's state_dict
+    ref_sd = ref_mod.MonoRecModel().state_dict()
+    out["state_keys"] = np.array(list(ref_sd.keys()))
+    out["state_shapes"] = np.array([",".join(str(int(v)) for v in t.shape) for t in ref_sd.values()])
     np.savez_compressed(HERE / "model_synth_small.npz", **out)
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size // 1024, "KiB")

@@ -1,0 +1,64 @@
+"""Host-side logic that needs no GPU: checkpoint contract, padding arithmetic, descriptor ABI, weight packing."""
+import ctypes
+
+import pytest
+import torch
+
+
+def test_reference_checkpoint_loads(tmp_path):
+    """Checkpoint contract (base/base_trainer.py:142-150, utils/util.py:244-248): DataParallel-prefixed state_dict."""
+    from monorec_b200.model import MonoRecModel
+    from monorec_b200.synthetic import seeded_state_dict
+    src = MonoRecModel()
+    sd = seeded_state_dict(src, seed=3, gain=1.0)
+    torch.save({"arch": "DataParallel", "state_dict": {"module." + k: v for k, v in sd.items()}}, tmp_path / "cp.pth")
+    m = MonoRecModel(checkpoint_location=[tmp_path / "cp.pth"])
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    torch.save({"arch": "MonoRecModel", "state_dict": sd}, tmp_path / "cp2.pth")
+    m2 = MonoRecModel(mask_cp_loc=tmp_path / "cp2.pth", depth_cp_loc=tmp_path / "cp2.pth")
+    assert torch.equal(m2.att_module.classifier[0].weight, sd["att_module.classifier.0.weight"])
+    assert torch.equal(m2.depth_module.dec[4][2].bias, sd["depth_module.dec.4.2.bias"])
+
+
+def test_same_padding_matches_reference_formula():
+    from monorec_b200.conv import same_pad_before
+    from oracle.convnet_oracle import same_pad
+    for n in (16, 17, 32, 33, 64, 255, 256):
+        for k in (1, 2, 3, 5, 7):
+            for s in (1, 2):
+                assert same_pad_before(n, k, s) == same_pad(n, k, s)[0]
+
+
+def test_conv_desc_abi_matches_library():
+    from monorec_b200 import _lib
+    from monorec_b200.conv import ConvDesc
+    assert ctypes.sizeof(ConvDesc) == _lib.load().mr_sizeof_conv_desc()
+
+
+def test_convT_subkernels_reproduce_conv_transpose():
+    """The four sub-pixel 2x2 kernels of pack_convT_k4s2 == ConvTranspose2d(k4,s2) + centre crop (layers.py:380-400)."""
+    import torch.nn.functional as F
+    from monorec_b200.conv import pack_convT_k4s2
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 5, 6, 7, generator=g)
+    w = torch.randn(5, 4, 4, 4, generator=g)
+    ref = F.conv_transpose2d(x, w, stride=2)[:, :, 1:-1, 1:-1]
+    out = torch.zeros_like(ref)
+    for (py, px), sub in pack_convT_k4s2(w).items():          # sub: [2][2][Cin][Cout]
+        wk = sub.permute(3, 2, 0, 1)                           # (Cout, Cin, 2, 2) correlation kernel
+        xp = F.pad(x, (1 - px, px, 1 - py, py))
+        out[:, :, py::2, px::2] = F.conv2d(xp, wk)
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_unsupported_reference_options_raise():
+    from monorec_b200.model import MonoRecModel
+    for kw in ({"simple_mask": True}, {"depth_large_model": True}, {"augmentation": "depth"}, {"use_ssim": False},
+               {"cv_patch_size": 5}, {"sfcv_mult_mask": False}):
+        with pytest.raises(NotImplementedError):
+            MonoRecModel(**kw)
+    m = MonoRecModel(pretrain_mode=2)
+    assert hasattr(m, "att_module") and not hasattr(m, "depth_module")
+    m = MonoRecModel(pretrain_mode=1)
+    assert hasattr(m, "depth_module") and not hasattr(m, "att_module")

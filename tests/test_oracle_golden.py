@@ -44,3 +44,24 @@ def test_plane_depths_order():
     z = O.plane_depths(0.33, 0.0025, 32)
     assert abs(z[0].item() - 400.0) < 1e-2 and abs(z[-1].item() - 1 / 0.33) < 1e-5
     assert torch.all(z[1:] < z[:-1])
+
+
+@pytest.mark.parametrize("gain_tag,gain", [("g1", 1.0), ("g07", 0.7)])
+def test_convnet_oracle_matches_reference_model(gain_tag, gain):
+    """oracle/convnet_oracle.py (+ the cost-volume oracle) vs the unmodified reference MonoRecModel forward."""
+    from monorec_b200.model import MonoRecModel
+    from monorec_b200.synthetic import make_inputs, seeded_state_dict
+    from oracle import convnet_oracle as CO
+    from tests.helpers import GOLDEN
+    g = np.load(GOLDEN / "model_synth_small.npz")
+    B, nF, D, H, W, seed, wseed = [int(v) for v in g["cfg"]]
+    model = MonoRecModel()
+    assert list(model.state_dict().keys()) == list(g["state_keys"])          # checkpoint contract, SURVEY.md §8b
+    assert [",".join(str(int(v)) for v in t.shape) for t in model.state_dict().values()] == list(g["state_shapes"])
+    sd = seeded_state_dict(model, seed=wseed, gain=gain)
+    data = make_inputs(B, nF, H, W, seed=seed)
+    cv, sf = O.cost_volume_torch(data, steps=D)
+    out = CO.monorec_forward(sd, data, cv, sf)
+    assert np.abs(out["cv_mask"].numpy() - g[f"{gain_tag}_cv_mask"]).max() < 2e-5
+    for i, p in enumerate(out["predicted_inverse_depths"]):
+        assert np.abs(p.numpy() - g[f"{gain_tag}_depth{i}"]).max() < 2e-5, i
