@@ -124,6 +124,11 @@ typedef struct mr_conv_desc {
 } mr_conv_desc;
 
 int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
+/* Same descriptor on the tensor cores (tcgen05, kind::tf32: TF32 products, fp32 accumulation in TMEM, fp32 storage).
+ * `weight` is packed as [kh*kw][n_pad][k_pad] (K contiguous): Cout padded to n_pad (multiple of 16, <= 256), every source
+ * padded to a multiple of 32 channels (k_pad = sum).  Needs src_c[i] % 4 == 0 and upsample2 == 0 (nearest-x2 upsampling is
+ * expressed as sub-pixel convolutions on this path).  round_out: round stored activations to TF32 (nearest). */
+int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream);
 /* sizeof(mr_conv_desc) as compiled into the library (bindings check their mirror of the struct against it). */
 int mr_sizeof_conv_desc(void);
 

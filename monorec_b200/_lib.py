@@ -25,6 +25,7 @@ SIGNATURES = {
     "mr_cost_volume_host": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float] * 3 + [c_void_p, c_longlong]),
     "mr_conv2d_nhwc": (c_int, [c_void_p, c_void_p]),
     "mr_sizeof_conv_desc": (c_int, []),
+    "mr_conv2d_nhwc_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "mr_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mr_maxpool2_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mr_max_over_frames": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p]),

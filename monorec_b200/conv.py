@@ -12,9 +12,22 @@ import torch
 
 from . import _lib
 
+import os
+
 MAX_SRC = 3
 ACT_NONE, ACT_LEAKY, ACT_SIGMOID, ACT_ABSTANH = 0, 1, 2, 3
 LEAKY_SLOPE = 0.1  # model/layers.py:290, 318, 381
+KC = 32            # channels per K chunk of the tensor-core kernel (csrc/conv_tc.cu)
+
+# Arithmetic of the dense-contraction layers: "tf32" = tcgen05 tensor cores (kind::tf32, fp32 accumulate, fp32 storage),
+# "fp32" = CUDA-core FMA kernel (bit-level parity path).  1-channel heads always use the fp32 kernel.
+MODE = os.environ.get("MONOREC_B200_CONV", "tf32").lower()
+
+
+def set_mode(mode):
+    global MODE
+    assert mode in ("tf32", "fp32")
+    MODE = mode
 
 
 class ConvDesc(ctypes.Structure):
@@ -166,3 +179,133 @@ def mask_volume(volume, mask):
         _lib.check(lib.mr_mask_volume(volume.data_ptr(), mask.data_ptr(), out.data_ptr(), B, D, H * W, _stream(volume)),
                    "mr_mask_volume")
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# layer objects: weights packed once for both kernels, dispatch by MODE
+# --------------------------------------------------------------------------------------------------------------------
+def _round_tf32(w):
+    """Round-to-nearest onto the TF32 grid (10 explicit mantissa bits); the tensor core truncates the rest."""
+    bits = w.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def pack_tc_weight(w, src_c):
+    """Correlation kernel (Cout, Cin, kh, kw) -> [kh*kw][n_pad][k_pad] K-major, every source padded to a multiple of 32
+    channels (zero rows) and Cout padded to a multiple of 16, values rounded to TF32."""
+    Cout, Cin, kh, kw = w.shape
+    assert sum(src_c) == Cin
+    n_pad = ((Cout + 15) // 16) * 16
+    k_pad = sum(((c + KC - 1) // KC) * KC for c in src_c)
+    out = torch.zeros(kh * kw, n_pad, k_pad, device=w.device, dtype=torch.float32)
+    wt = w.detach().to(torch.float32).permute(2, 3, 0, 1).reshape(kh * kw, Cout, Cin)
+    ci = ko = 0
+    for c in src_c:
+        out[:, :Cout, ko:ko + c] = wt[:, :, ci:ci + c]
+        ci += c
+        ko += ((c + KC - 1) // KC) * KC
+    return _round_tf32(out), n_pad, k_pad
+
+
+class PackedConv:
+    """One convolution of the engine with its weights in both kernel layouts."""
+
+    def __init__(self, weight, bias, src_c, stride=(1, 1), act=ACT_NONE, act_a=0.0, act_b=1.0, pad=None, out_step=(1, 1),
+                 out_off=(0, 0), allow_tc=True):
+        w = weight.detach().to(torch.float32)
+        self.cout, self.cin, self.kh, self.kw = w.shape
+        self.src_c = tuple(int(c) for c in src_c)
+        self.stride, self.pad, self.out_step, self.out_off = stride, pad, out_step, out_off
+        self.act, self.act_a, self.act_b = act, act_a, act_b
+        self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        self.w32 = pack_conv_weight(w)
+        self.tc_ok = allow_tc and self.cout <= 256 and self.cout >= 8 and all(c % 4 == 0 for c in self.src_c)
+        self._wtc = None
+        self._w_src = w
+
+    def wtc(self):
+        if self._wtc is None:
+            self._wtc = pack_tc_weight(self._w_src, self.src_c)
+        return self._wtc
+
+    def __call__(self, srcs, out=None, out_hw=None, final=False):
+        assert tuple(s.shape[3] for s in srcs) == self.src_c, (tuple(s.shape[3] for s in srcs), self.src_c)
+        if MODE == "tf32" and self.tc_ok:
+            return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=not final)
+        return conv2d(srcs, self.w32, self.bias, self.kh, self.kw, stride=self.stride, act=self.act, act_a=self.act_a,
+                      act_b=self.act_b, out=out, pad=self.pad, out_hw=out_hw, out_step=self.out_step, out_off=self.out_off)
+
+
+def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True):
+    """Tensor-core launch (csrc/conv_tc.cu) of a PackedConv."""
+    lib = _lib.load()
+    x0 = srcs[0]
+    B, Hs, Ws, _ = x0.shape
+    sy, sx = L.stride
+    pad = L.pad if L.pad is not None else (same_pad_before(Hs, L.kh, sy), same_pad_before(Ws, L.kw, sx))
+    if out_hw is None:
+        out_hw = (math.ceil(Hs / sy), math.ceil(Ws / sx))
+    Ho, Wo = out_hw
+    if out is None:
+        out = torch.empty(B, Ho * L.out_step[0], Wo * L.out_step[1], L.cout, device=x0.device, dtype=torch.float32)
+    wtc, n_pad, k_pad = L.wtc()
+    d = ConvDesc()
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        assert s.is_cuda and s.dtype == torch.float32 and s.is_contiguous()
+        assert s.shape[:3] == x0.shape[:3]
+        d.src[i] = s.data_ptr()
+        d.src_c[i] = s.shape[3]
+    d.B, d.Hs, d.Ws, d.upsample2 = B, Hs, Ws, 0
+    d.kh, d.kw, d.sy, d.sx, d.pad_t, d.pad_l = L.kh, L.kw, sy, sx, pad[0], pad[1]
+    d.Ho, d.Wo, d.Cout = Ho, Wo, L.cout
+    d.weight = wtc.data_ptr()
+    d.bias = L.bias.data_ptr() if L.bias is not None else None
+    d.dst = out.data_ptr()
+    d.dst_H, d.dst_W, d.dst_c, d.dst_coff = out.shape[1], out.shape[2], out.shape[3], 0
+    d.oy_step, d.ox_step, d.oy_off, d.ox_off = L.out_step[0], L.out_step[1], L.out_off[0], L.out_off[1]
+    d.act, d.act_a, d.act_b = L.act, L.act_a, L.act_b
+    with torch.cuda.device(x0.device):
+        _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
+    return out
+
+
+class PackedSubpixel:
+    """Four sub-pixel convolutions writing the (2H, 2W) output with step 2: Refine's ConvTranspose2d(k4, s2) + crop
+    (model/layers.py:380-400) and Upconv's nearest-x2 + pad(0,1,0,1) + 2x2 conv (:338-356)."""
+
+    def __init__(self, subs):
+        self.subs = subs   # list of PackedConv
+
+    def __call__(self, srcs):
+        x0 = srcs[0]
+        B, Hs, Ws, _ = x0.shape
+        out = torch.empty(B, 2 * Hs, 2 * Ws, self.subs[0].cout, device=x0.device, dtype=torch.float32)
+        for L in self.subs:
+            L(srcs, out=out, out_hw=(Hs, Ws))
+        return out
+
+
+def refine_layer(conv2d_t, src_c, act=ACT_LEAKY, act_a=LEAKY_SLOPE):
+    w = conv2d_t.weight.detach().to(torch.float32)       # (Cin, Cout, 4, 4)
+    taps = {0: (3, 1), 1: (2, 0)}                        # see pack_convT_k4s2
+    subs = []
+    for py in (0, 1):
+        for px in (0, 1):
+            sub = w[:, :, list(taps[py]), :][:, :, :, list(taps[px])].permute(1, 0, 2, 3).contiguous()  # (Cout,Cin,2,2)
+            subs.append(PackedConv(sub, conv2d_t.bias, src_c, act=act, act_a=act_a, pad=(1 - py, 1 - px),
+                                   out_step=(2, 2), out_off=(py, px)))
+    return PackedSubpixel(subs)
+
+
+def upconv_layer(conv, src_c):
+    """out[2oy+py, 2ox+px] of nearest-x2 + 2x2 conv: even phases see both taps on the same input pixel (weights add up),
+    odd phases see input pixels o and o+1 (zero beyond the border = the reference's trailing pad)."""
+    w = conv.weight.detach().to(torch.float32)           # (Cout, Cin, 2, 2)
+    subs = []
+    for py in (0, 1):
+        wy = w if py == 1 else w.sum(2, keepdim=True)
+        for px in (0, 1):
+            wyx = wy if px == 1 else wy.sum(3, keepdim=True)
+            subs.append(PackedConv(wyx.contiguous(), conv.bias, src_c, pad=(0, 0), out_step=(2, 2), out_off=(py, px)))
+    return PackedSubpixel(subs)

@@ -1,0 +1,345 @@
+// Convolution engine, tensor-core path: implicit GEMM on tcgen05 (5th-gen tensor cores) for sm_100a.
+//
+//   D[128 pixels x Cout] (fp32, TMEM)  +=  A[128 pixels x 32 ch] (smem, TMA)  x  B[Cout x 32 ch]^T (smem, TMA)     kind::tf32
+//
+// One CTA owns an 8x16 tile of output pixels (UMMA M = 128) and all Cout (UMMA N = Cout padded to 16, <= 256).  The K
+// loop runs over (filter tap, concatenated source, 32-channel chunk):
+//   * the A operand of a tap is the NHWC input tile shifted by the tap offset, fetched by ONE 4-D TMA box
+//     {32 ch, 16 px, 8 px, 1 img} (traversal stride = conv stride).  Out-of-bounds elements are zero-filled by the TMA unit,
+//     which IS the reference's PadSameConv2d (model/layers.py:220-252); channel concatenation (torch.cat,
+//     monorec_model.py:372-380, :541-545) is just one tensor map per source;
+//   * the B operand is the matching [Cout x 32] slice of the packed weights (2-D TMA);
+//   * both land in 128-byte-swizzled K-major shared-memory tiles that tcgen05.mma consumes through smem descriptors.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (tcgen05.ld -> bias -> activation -> NHWC store, optional sub-pixel placement).
+// Pipelines: smem full/empty mbarrier ring between TMA and MMA; one tmem-full mbarrier between MMA and epilogue.
+//
+// Reference being replaced: nn.Conv2d / nn.ConvTranspose2d + bias + LeakyReLU of model/layers.py:289-400 as used by
+// MaskModule / DepthModule (model/monorec/monorec_model.py:287-385, :476-557).
+#include "mr_common.cuh"
+#include <cuda.h>
+#include <cstdint>
+
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kKC = 32;                 // fp32 channels per K chunk = one 128-byte swizzle row
+constexpr int kTileH = 8, kTileW = 16;  // 128 output pixels per CTA
+constexpr uint32_t kABytes = 128 * 128; // A stage: 128 rows x 128 B
+
+struct TcArgs {
+    int n_src;
+    int chunks[MR_CONV_MAX_SRC];   // 32-channel chunks per source
+    int kh, kw, sy, sx, pad_t, pad_l;
+    int Ho, Wo, Cout, n_pad, tiles_x, stages;
+    uint32_t tmem_cols;
+    const float* bias;
+    float* dst;
+    int dst_H, dst_W, dst_c, dst_coff, oy_step, ox_step, oy_off, ox_off;
+    int act;
+    float act_a, act_b;
+    int round_out;                 // 1: round stored activations to TF32 (nearest) so the next layer's truncation is exact
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float act_fn(float v, int act, float a, float b) {
+    switch (act) {
+        case MR_ACT_LEAKY: return v >= 0.f ? v : a * v;
+        case MR_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+        case MR_ACT_ABSTANH: return fmaf(b, fabsf(tanhf(v)), a);
+        default: return v;
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * 8 + 1];   // full[stages], empty[stages], tmem_full
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
+    const uint32_t stage_bytes = kABytes + b_bytes;
+    const int stages = a.stages;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), tfull = smem_u32(&bars[16]);
+
+    const int tile_y = blockIdx.x / a.tiles_x, tile_x = blockIdx.x - tile_y * a.tiles_x;
+    const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
+    const int b = blockIdx.y;
+    const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
+    const int total = a.kh * a.kw * chunks_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA0);
+        if (a.n_src > 1) prefetch_tmap(&tmA1);
+        if (a.n_src > 2) prefetch_tmap(&tmA2);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1) {   // TMEM allocation (power of two >= 32 columns), address published through shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(a.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int ky = 0; ky < a.kh; ++ky)
+                for (int kx = 0; kx < a.kw; ++kx) {
+                    const int ix0 = ox0 * a.sx - a.pad_l + kx, iy0 = oy0 * a.sy - a.pad_t + ky;
+                    int kbase = 0;
+                    for (int s = 0; s < a.n_src; ++s) {
+                        const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
+                        for (int j = 0; j < a.chunks[s]; ++j, ++it) {
+                            const int st = it % stages;
+                            const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                            mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                            const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
+                            mbar_expect_tx(full0 + 8 * st, stage_bytes);
+                            tma_load_4d(sa, tm, full0 + 8 * st, j * kKC, ix0, iy0, b);
+                            tma_load_2d(sb, &tmB, full0 + 8 * st, kbase + j * kKC, (ky * a.kw + kx) * a.n_pad);
+                        }
+                        kbase += a.chunks[s] * kKC;
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6), a/b format TF32 = 2 @[7,10)/[10,13),
+        // K-major A and B, N >> 3 @[17,23), M >> 4 @[24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+        for (int it = 0; it < total; ++it) {
+            const int st = it % stages;
+            const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            mbar_wait(full0 + 8 * st, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
+                const uint64_t da = make_desc(sa), db = make_desc(sb);
+#pragma unroll
+                for (int k = 0; k < kKC / 8; ++k)   // UMMA K = 8 for tf32: advance 32 bytes inside the swizzle row
+                    umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+                umma_commit(empty0 + 8 * st);               // frees the smem stage once these MMAs have read it
+                if (it == total - 1) umma_commit(tfull);    // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> bias/activation -> NHWC =====================
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int p = 32 * q + lane;            // pixel (= accumulator row) of this thread
+        const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
+        const bool live = (oy < a.Ho) && (ox < a.Wo);
+        float* op = a.dst + (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+                                a.dst_c + a.dst_coff;
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16);
+        const bool vec_ok = ((a.dst_c | a.dst_coff) & 3) == 0;
+        for (int n0 = 0; n0 < a.n_pad; n0 += 8) {
+            uint32_t r[8];
+            tmem_ld8(trow + (uint32_t)n0, r);
+            if (!live) continue;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + j;
+                float x = __uint_as_float(r[j]) + ((a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
+                x = act_fn(x, a.act, a.act_a, a.act_b);
+                if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+                v[j] = x;
+            }
+            if (vec_ok && n0 + 8 <= a.Cout) {
+                *reinterpret_cast<float4*>(op + n0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(op + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (n0 + j < a.Cout) op[n0 + j] = v[j];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(a.tmem_cols));
+    }
+}
+
+// ---- host side: tensor maps ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;   // benign race: every thread resolves the same pointer
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream) {
+    MR_REQUIRE(desc != nullptr, "mr_conv2d_nhwc_tc: null descriptor");
+    const mr_conv_desc& d = *desc;
+    MR_REQUIRE(d.n_src >= 1 && d.n_src <= MR_CONV_MAX_SRC, "mr_conv2d_nhwc_tc: n_src=%d out of range", d.n_src);
+    MR_REQUIRE(d.upsample2 == 0, "mr_conv2d_nhwc_tc: upsample-on-read is expressed as sub-pixel convolutions on this path");
+    MR_REQUIRE(d.weight && d.dst, "mr_conv2d_nhwc_tc: null weight/dst");
+    MR_REQUIRE(d.Cout >= 1 && d.Cout <= 256 && n_pad >= d.Cout && n_pad <= 256 && (n_pad % 16) == 0,
+               "mr_conv2d_nhwc_tc: Cout=%d n_pad=%d unsupported (Cout <= 256, n_pad multiple of 16)", d.Cout, n_pad);
+    MR_REQUIRE(d.B >= 1 && d.B <= 65535 && d.Hs >= 1 && d.Ws >= 1 && d.Ho >= 1 && d.Wo >= 1, "mr_conv2d_nhwc_tc: bad shape");
+    MR_REQUIRE(d.kh >= 1 && d.kw >= 1 && d.sy >= 1 && d.sx >= 1 && d.sy <= 4 && d.sx <= 4, "mr_conv2d_nhwc_tc: bad kernel/stride");
+    MR_REQUIRE(d.dst_coff >= 0 && d.dst_coff + d.Cout <= d.dst_c, "mr_conv2d_nhwc_tc: channel slice out of range");
+    MR_REQUIRE((d.Ho - 1) * d.oy_step + d.oy_off < d.dst_H && (d.Wo - 1) * d.ox_step + d.ox_off < d.dst_W,
+               "mr_conv2d_nhwc_tc: output placement out of range");
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) {
+        mr::set_error("mr_conv2d_nhwc_tc: cuTensorMapEncodeTiled is not available from this driver");
+        return MR_ENOSUPPORT;
+    }
+    TcArgs a{};
+    a.n_src = d.n_src;
+    int ksum = 0;
+    CUtensorMap tmA[MR_CONV_MAX_SRC];
+    for (int s = 0; s < d.n_src; ++s) {
+        const int C = d.src_c[s];
+        MR_REQUIRE(d.src[s] != nullptr && C >= 4 && (C % 4) == 0,
+                   "mr_conv2d_nhwc_tc: source %d needs a channel count that is a multiple of 4 (got %d)", s, C);
+        MR_REQUIRE((reinterpret_cast<uintptr_t>(d.src[s]) & 15) == 0, "mr_conv2d_nhwc_tc: source %d is not 16-byte aligned", s);
+        a.chunks[s] = (C + kKC - 1) / kKC;
+        ksum += a.chunks[s] * kKC;
+        const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)d.Ws, (cuuint64_t)d.Hs, (cuuint64_t)d.B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)d.Ws * C * 4, (cuuint64_t)d.Hs * d.Ws * C * 4};
+        // with a traversal stride s the box spans box/s loaded elements: 16 (8) output pixels need a span of 16*s (8*s)
+        const cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)(kTileW * d.sx), (cuuint32_t)(kTileH * d.sy), 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)d.sx, (cuuint32_t)d.sy, 1};
+        CUresult r = encode(&tmA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.src[s]), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            mr::set_error("mr_conv2d_nhwc_tc: cuTensorMapEncodeTiled(A%d) failed with CUresult %d", s, (int)r);
+            return MR_EINVAL;
+        }
+    }
+    for (int s = d.n_src; s < MR_CONV_MAX_SRC; ++s) tmA[s] = tmA[0];
+    MR_REQUIRE(ksum == k_pad, "mr_conv2d_nhwc_tc: packed weight K (%d) does not match the sources (%d)", k_pad, ksum);
+    MR_REQUIRE((reinterpret_cast<uintptr_t>(d.weight) & 15) == 0, "mr_conv2d_nhwc_tc: weights are not 16-byte aligned");
+    CUtensorMap tmB;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)d.kh * d.kw * n_pad};
+        const cuuint64_t gstr[1] = {(cuuint64_t)k_pad * 4};
+        const cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)n_pad};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d.weight), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            mr::set_error("mr_conv2d_nhwc_tc: cuTensorMapEncodeTiled(B) failed with CUresult %d", (int)r);
+            return MR_EINVAL;
+        }
+    }
+    a.kh = d.kh; a.kw = d.kw; a.sy = d.sy; a.sx = d.sx; a.pad_t = d.pad_t; a.pad_l = d.pad_l;
+    a.Ho = d.Ho; a.Wo = d.Wo; a.Cout = d.Cout; a.n_pad = n_pad;
+    a.tiles_x = (d.Wo + kTileW - 1) / kTileW;
+    const int tiles = a.tiles_x * ((d.Ho + kTileH - 1) / kTileH);
+    const int total = d.kh * d.kw * (a.chunks[0] + a.chunks[1] + a.chunks[2]);
+    const size_t stage_bytes = (size_t)kABytes + (size_t)n_pad * 128;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages > total) stages = total;
+    if (stages < 1) stages = 1;
+    a.stages = stages;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)n_pad) cols <<= 1;
+    a.tmem_cols = cols;
+    a.bias = d.bias; a.dst = d.dst;
+    a.dst_H = d.dst_H; a.dst_W = d.dst_W; a.dst_c = d.dst_c; a.dst_coff = d.dst_coff;
+    a.oy_step = d.oy_step; a.ox_step = d.ox_step; a.oy_off = d.oy_off; a.ox_off = d.ox_off;
+    a.act = d.act; a.act_a = d.act_a; a.act_b = d.act_b; a.round_out = round_out;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    dim3 grid(tiles, d.B);
+    conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+    MR_LAUNCH_CHECK("conv_tc_kernel");
+    return MR_OK;
+}

@@ -71,8 +71,8 @@ class _Packed:
         return self.data
 
 
-def _w(conv):
-    return C.pack_conv_weight(conv.weight), conv.bias.detach().to(torch.float32).contiguous()
+def _leaky(conv, src_c, stride=(1, 1)):
+    return C.PackedConv(conv.weight, conv.bias, src_c, stride=stride, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -127,13 +127,18 @@ class MaskModule(nn.Module):
         self._packed = _Packed()
 
     def _build(self):
+        e, d, fc = self._cv_enc_feat_chns, self._dec_feat_chns, self.feat_chns
         p = {}
         for lvl, seq in enumerate(self.enc):
             mods = [m for m in seq if isinstance(m, ConvReLU)]
-            p[f"enc{lvl}"] = [_w(m.conv) for m in mods]
+            p[f"enc{lvl}"] = [_leaky(m.conv, (m.conv.in_channels,)) for m in mods]
+        up_src = [(e[4], fc[3]), (d[0],), (d[1],), (d[2],)]
+        cat_src = [(e[3], fc[2], d[0]), (e[2], fc[1], d[0]), (e[1], fc[0], d[1]), (e[0], d[2])]
         for i, seq in enumerate(self.dec):
-            p[f"dec{i}"] = [_w(seq[0].conv), _w(seq[1].conv), _w(seq[2].conv)]
-        p["cls"] = _w(self.classifier[0])
+            p[f"dec{i}"] = [C.upconv_layer(seq[0].conv, up_src[i]), _leaky(seq[1].conv, cat_src[i]),
+                            _leaky(seq[2].conv, (seq[2].conv.in_channels,))]
+        cls = self.classifier[0]
+        p["cls"] = C.PackedConv(cls.weight, cls.bias, (cls.in_channels,), act=C.ACT_SIGMOID, allow_tc=False)
         return p
 
     def forward(self, data_dict):
@@ -154,27 +159,24 @@ class MaskModule(nn.Module):
         for lvl in range(5):
             if lvl > 0:
                 x = C.maxpool2(x)
-            for (w, b) in P[f"enc{lvl}"]:
-                x = C.conv2d([x], w, b, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
+            for layer in P[f"enc{lvl}"]:
+                x = layer([x])
             cv_feats.append(C.max_over_frames(x, nF))
         img = [C.nchw_to_nhwc(f.to(torch.float32)) for f in feats_nchw[:4]]
         if not self.use_features:
             img = [torch.zeros_like(t) for t in img]
         x = None
         for i in range(4):
-            (wu, bu), (w1, b1), (w2, b2) = P[f"dec{i}"]
-            up_src = [cv_feats[4], img[3]] if i == 0 else [x]
-            x = C.conv2d(up_src, wu, bu, 2, 2, upsample2=True)                      # Upconv: no activation
+            up, c1, c2 = P[f"dec{i}"]
+            x = up([cv_feats[4], img[3]] if i == 0 else [x])                        # Upconv: no activation
             if i == 0:
                 cat = [cv_feats[3], img[2], x]
             elif i == 3:
                 cat = [cv_feats[0], x]
             else:
                 cat = [cv_feats[3 - i], img[2 - i], x]
-            x = C.conv2d(cat, w1, b1, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
-            x = C.conv2d([x], w2, b2, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
-        wc, bc = P["cls"]
-        m = C.conv2d([x], wc, bc, 1, 1, act=C.ACT_SIGMOID)                           # [B,H,W,1]
+            x = c2([c1(cat)])
+        m = P["cls"]([x], final=True)                                                # [B,H,W,1]
         data_dict["cv_mask"] = m.view(B, 1, H, W)                                    # C == 1: NHWC == NCHW
         return data_dict
 
@@ -209,30 +211,36 @@ class DepthModule(nn.Module):
         self.out_range = (0.0, 1.0)   # (a, b): heads emit a + b * |tanh|; MonoRecModel folds the inverse-depth affine in
 
     def _build(self):
-        def cr2(m):
-            return (_w(m.conv_y), _w(m.conv_x), m.kernel_size, m.stride)
+        e, d, fc = self._cv_enc_feat_chns, self._dec_feat_chns, self.feat_chns
 
-        def rf(m):
-            return (C.pack_convT_k4s2(m.conv2d_t.weight), m.conv2d_t.bias.detach().to(torch.float32).contiguous())
-        p = {"enc": [(cr2(s[0]), cr2(s[1])) for s in self.enc]}
-        p["dec0"] = rf(self.dec[0])
-        p["dec1"] = (rf(self.dec[1][0]), cr2(self.dec[1][1]))
-        p["dec2"] = (rf(self.dec[2][0]), cr2(self.dec[2][1]))
-        p["dec3"] = rf(self.dec[3])
-        p["dec4"] = (cr2(self.dec[4][0]), _w(self.dec[4][2]))
-        p["heads"] = [_w(s[1]) for s in self.predictors]
+        def cr2(m, src_c, pad_in=0):
+            wy = m.conv_y.weight
+            if pad_in:   # zero input channels appended so that the NHWC input is 16-byte aligned per pixel
+                wy = torch.cat([wy, wy.new_zeros(wy.shape[0], pad_in, wy.shape[2], wy.shape[3])], 1)
+            return (C.PackedConv(wy, m.conv_y.bias, src_c, stride=(m.stride, 1), act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE),
+                    _leaky(m.conv_x, (m.conv_x.in_channels,), stride=(1, m.stride)))
+        cin0 = self._in_channels
+        self._cin0_pad = (-cin0) % 4
+        p = {"enc": []}
+        for i, s in enumerate(self.enc):
+            first = cr2(s[0], (cin0 + self._cin0_pad,), self._cin0_pad) if i == 0 else cr2(s[0], (e[i - 1],))
+            p["enc"].append((first, cr2(s[1], (e[i],))))
+        p["dec0"] = C.refine_layer(self.dec[0].conv2d_t, (e[4],))
+        p["dec1"] = (C.refine_layer(self.dec[1][0].conv2d_t, (e[3], fc[2], d[0])), cr2(self.dec[1][1], (d[1],)))
+        p["dec2"] = (C.refine_layer(self.dec[2][0].conv2d_t, (e[2], fc[1], d[1])), cr2(self.dec[2][1], (d[2],)))
+        p["dec3"] = C.refine_layer(self.dec[3].conv2d_t, (e[1], fc[0], d[2]))
+        p["dec4"] = (cr2(self.dec[4][0], (e[0], d[3])), _leaky(self.dec[4][2], (d[4],)))
+        p["heads"] = [s[1] for s in self.predictors]
         return p
 
     @staticmethod
     def _cr2(srcs, pk):
-        (wy, by), (wx, bx), k, s = pk
-        t = C.conv2d(srcs, wy, by, k, 1, stride=(s, 1), act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
-        return C.conv2d([t], wx, bx, 1, k, stride=(1, s), act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)
+        return pk[1]([pk[0](srcs)])
 
-    def _head(self, x, wb):
-        w, b = wb
+    def _head(self, x, conv):
         a, s = self.out_range
-        y = C.conv2d([x], w, b, 3, 3, act=C.ACT_ABSTANH, act_a=a, act_b=s)
+        head = C.PackedConv(conv.weight, conv.bias, (conv.in_channels,), act=C.ACT_ABSTANH, act_a=a, act_b=s, allow_tc=False)
+        y = head([x], final=True)
         B, H, W, _ = y.shape
         return y.view(B, 1, H, W)
 
@@ -246,37 +254,35 @@ class DepthModule(nn.Module):
         B, D, H, W = cv.shape
         # cat(cost_volume, keyframe) (:531); when MonoRecModel passes the unmasked volume plus `_cv_mask_for_depth`
         # the (1 - cv_mask) product of :713 is applied during the layout change
-        x = torch.empty(B, H, W, D + 3, device=cv.device, dtype=torch.float32)
+        cpad = self._cin0_pad
+        x = (torch.zeros if cpad else torch.empty)(B, H, W, D + 3 + cpad, device=cv.device, dtype=torch.float32)
         C.nchw_to_nhwc(cv.to(torch.float32), out=x, out_coff=0, one_minus=data_dict.get("_cv_mask_for_depth"))
         C.nchw_to_nhwc(keyframe.to(torch.float32), out=x, out_coff=D)
         img = [C.nchw_to_nhwc(f.to(torch.float32)) for f in feats_nchw[:3]]
         feats = []
         for (p0, p1) in P["enc"]:
-            x = self._cr2([x], p0)
-            x = self._cr2([x], p1)
+            x = self._cr2([self._cr2([x], p0)], p1)
             feats.append(x)
+        heads = P["heads"]
         preds = []
-        sw, sb = P["dec0"]
-        x = C.conv_transpose_k4s2_crop([feats[4]], sw, sb)                               # 256 @ 1/8
-        preds.insert(0, self._head(x, P["heads"][0]))
-        (sw, sb), pk = P["dec1"]
-        x = self._cr2([C.conv_transpose_k4s2_crop([feats[3], img[2], x], sw, sb)], pk)    # 128 @ 1/4
-        preds.insert(0, self._head(x, P["heads"][1]))
-        (sw, sb), pk = P["dec2"]
-        x = self._cr2([C.conv_transpose_k4s2_crop([feats[2], img[1], x], sw, sb)], pk)    # 64 @ 1/2
-        preds.insert(0, self._head(x, P["heads"][2]))
-        sw, sb = P["dec3"]
-        x = C.conv_transpose_k4s2_crop([feats[1], img[0], x], sw, sb)                     # 48 @ full
-        pk, (w2, b2) = P["dec4"]
-        x = self._cr2([feats[0], x], pk)
-        x = C.conv2d([x], w2, b2, 3, 3, act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE)            # 24 @ full
-        preds.insert(0, self._head(x, P["heads"][3]))
+        x = P["dec0"]([feats[4]])                                                     # 256 @ 1/8
+        preds.insert(0, self._head(x, heads[0]))
+        up, pk = P["dec1"]
+        x = self._cr2([up([feats[3], img[2], x])], pk)                                # 128 @ 1/4
+        preds.insert(0, self._head(x, heads[1]))
+        up, pk = P["dec2"]
+        x = self._cr2([up([feats[2], img[1], x])], pk)                                # 64 @ 1/2
+        preds.insert(0, self._head(x, heads[2]))
+        x = P["dec3"]([feats[1], img[0], x])                                          # 48 @ full
+        pk, last = P["dec4"]
+        x = last([self._cr2([feats[0], x], pk)])                                      # 24 @ full
+        preds.insert(0, self._head(x, heads[3]))
         data_dict["predicted_inverse_depths"] = preds
         return data_dict
 
     def predict_depth(self, x, scale):
         """API parity with the reference (:554-557); x is NHWC inside this implementation."""
-        return self._head(x, self._packed.get(self, self._build)["heads"][scale])
+        return self._head(x, self.predictors[scale][1])
 
 
 class MonoRecModel(nn.Module):
