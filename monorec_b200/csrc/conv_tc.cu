@@ -324,10 +324,12 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     const int tiles = a.tiles_x * ((d.Ho + kTileH - 1) / kTileH);
     const int total = d.kh * d.kw * (a.chunks[0] + a.chunks[1] + a.chunks[2]);
     const size_t stage_bytes = (size_t)kABytes + (size_t)n_pad * 128;
-    int stages = (int)((200 * 1024) / stage_bytes);
-    if (stages > 6) stages = 6;
+    // several CTAs per SM overlap one tile's epilogue with another tile's main loop (non-persistent kernel): keep the
+    // ring at ~72 KB so that three CTAs (two for the widest layers) are resident
+    int stages = (int)((72 * 1024) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 2) stages = 2;
     if (stages > total) stages = total;
-    if (stages < 1) stages = 1;
     a.stages = stages;
     uint32_t cols = 32;
     while (cols < (uint32_t)n_pad) cols <<= 1;

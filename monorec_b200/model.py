@@ -364,9 +364,10 @@ class MonoRecModel(nn.Module):
     def forward(self, data_dict):
         keyframe = data_dict["keyframe"]
         lo, hi = float(self.inv_depth_min_max[1]), float(self.inv_depth_min_max[0])
-        data_dict["inv_depth_min"] = keyframe.new_tensor([self.inv_depth_min_max[0]])
-        data_dict["inv_depth_max"] = keyframe.new_tensor([self.inv_depth_min_max[1]])
-        data_dict["cv_depth_steps"] = keyframe.new_tensor([self.cv_depth_steps], dtype=torch.int32)
+        # 1-element tensors like the reference's (:675-677); torch.full is a fill kernel (CUDA-graph capturable, no H2D copy)
+        data_dict["inv_depth_min"] = torch.full((1,), float(self.inv_depth_min_max[0]), device=keyframe.device, dtype=keyframe.dtype)
+        data_dict["inv_depth_max"] = torch.full((1,), float(self.inv_depth_min_max[1]), device=keyframe.device, dtype=keyframe.dtype)
+        data_dict["cv_depth_steps"] = torch.full((1,), int(self.cv_depth_steps), device=keyframe.device, dtype=torch.int32)
         data_dict["_cv_range"] = (lo, hi, int(self.cv_depth_steps))   # host copy: no .item() synchronisation
 
         with torch.no_grad():
@@ -405,3 +406,37 @@ class MonoRecModel(nn.Module):
         data_dict.pop("_cv_range", None)
         return data_dict
 
+
+
+class GraphedMonoRec:
+    """CUDA-graph replay of MonoRecModel.forward for a fixed input signature.
+
+    The forward is ~150 small launches; issued from Python it is bound by the host (SURVEY.md §3.5 "hidden syncs" are gone,
+    the launch overhead is not).  Capturing once and replaying removes the host from the loop.  Inputs are copied into
+    static buffers, outputs are the static tensors of the captured run (valid until the next call).
+    """
+
+    def __init__(self, model, example, warmup=2):
+        self.model = model
+        self.static_in = {k: ([t.clone() for t in v] if isinstance(v, (list, tuple)) else v.clone())
+                          for k, v in example.items() if torch.is_tensor(v) or isinstance(v, (list, tuple))}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                self.model(dict(self.static_in))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = self.model(dict(self.static_in))
+
+    def __call__(self, data):
+        for k, v in self.static_in.items():
+            if isinstance(v, list):
+                for dst, src in zip(v, data[k]):
+                    dst.copy_(src, non_blocking=True)
+            else:
+                v.copy_(data[k], non_blocking=True)
+        self.graph.replay()
+        return self.static_out
