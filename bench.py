@@ -41,43 +41,56 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clocks / throttle reasons through NVML every 20 ms while the timed region runs."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except OSError:
-            self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
+        self.stop.set()
+        if self.t is not None:
+            self.t.join(timeout=1)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.nv is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        nv = self.nv
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": [n for n, m in names.items() if bits & m],
+                "samples": len(sm)}
 
 
 def cpu_port_keyframes_per_s(repeats, threads=None):
@@ -126,11 +139,12 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-model", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -257,6 +271,36 @@ def main():
             line["e2e"] = {"value": world * B * e_steps / float(t.item()), "unit": "keyframes/s",
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
                            "api": "mr_cost_volume_host (C ABI, pinned host buffers, both volumes downloaded)"}
+
+    # ---- informational: the whole MonoRecModel.forward (cost volume + ResNet-18 + mask/depth conv stacks on the tensor
+    #      cores) replayed from a CUDA graph, batch sharded like above, per-rank result maps all-gathered over NCCL ----
+    if not args.no_full_model:
+        from monorec_b200 import conv as C
+        from monorec_b200.dist import all_gather_batch
+        from monorec_b200.model import GraphedMonoRec, MonoRecModel
+        torch.manual_seed(0)
+        model = MonoRecModel().to(dev).eval()          # random-init weights of the reference architecture
+        gm = GraphedMonoRec(model, sets[0])
+        fm_steps = 20
+        for i in range(3):
+            all_gather_batch(gm(sets[i % NSETS])["result"])
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(fm_steps):
+            res = all_gather_batch(gm(sets[i % NSETS])["result"])
+        f1.record()
+        barrier()
+        t = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            fms = float(t.item()) / fm_steps
+            line["full_model"] = {"value": world * B / (fms * 1e-3), "unit": "keyframes/s", "ms_per_forward": fms,
+                                  "batch_per_gpu": B, "conv_arithmetic": C.MODE, "gathered_result_shape": list(res.shape),
+                                  "what": "MonoRecModel.forward (CUDA-graph replay) + NCCL all-gather of result; "
+                                          "inputs resident, random-init weights"}
+        del gm, model
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores = cpu_port_keyframes_per_s(repeats=2)

@@ -134,6 +134,42 @@ __global__ void __launch_bounds__(kConvThreads) conv2d_nhwc_kernel(const mr_conv
     }
 }
 
+// Single-output-channel layers (1x1 mask classifier, 3x3 depth heads: monorec_model.py:340-343, :521-524): a per-pixel dot
+// product, HBM-bound -- not a dense contraction, so no tensor cores and no 32-wide channel tile.  One thread per output
+// pixel, float4 channel loads (adjacent pixels are adjacent in NHWC, so a warp streams one contiguous block per filter row).
+__global__ void __launch_bounds__(256) conv_cout1_kernel(const mr_conv_desc d) {
+    extern __shared__ float wsm[];   // [kh*kw][C]
+    const int C = d.src_c[0];
+    const int nw = d.kh * d.kw * C;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = __ldg(d.weight + i);
+    __syncthreads();
+    const size_t total = (size_t)d.B * d.Ho * d.Wo;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ox = (int)(idx % d.Wo);
+    const int oy = (int)((idx / d.Wo) % d.Ho);
+    const int b = (int)(idx / ((size_t)d.Wo * d.Ho));
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    for (int ky = 0; ky < d.kh; ++ky) {
+        const int iy = oy * d.sy - d.pad_t + ky;
+        if (iy < 0 || iy >= d.Hs) continue;
+        for (int kx = 0; kx < d.kw; ++kx) {
+            const int ix = ox * d.sx - d.pad_l + kx;
+            if (ix < 0 || ix >= d.Ws) continue;
+            const float4* p = reinterpret_cast<const float4*>(d.src[0] + (((size_t)b * d.Hs + iy) * d.Ws + ix) * C);
+            const float4* w = reinterpret_cast<const float4*>(wsm + (ky * d.kw + kx) * C);
+            for (int c = 0; c < C / 4; ++c) {
+                const float4 v = __ldg(p + c), q = w[c];
+                acc0 = fmaf(v.x, q.x, acc0); acc1 = fmaf(v.y, q.y, acc1);
+                acc2 = fmaf(v.z, q.z, acc2); acc3 = fmaf(v.w, q.w, acc3);
+            }
+        }
+    }
+    float v = (acc0 + acc1) + (acc2 + acc3) + (d.bias ? __ldg(d.bias) : 0.f);
+    const int dy = oy * d.oy_step + d.oy_off, dx = ox * d.ox_step + d.ox_off;
+    d.dst[(((size_t)b * d.dst_H + dy) * d.dst_W + dx) * d.dst_c + d.dst_coff] = apply_act(v, d.act, d.act_a, d.act_b);
+}
+
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int dst_c,
                                     int dst_coff, const float* __restrict__ oms) {
     // one CTA: 32 pixels x 32 channels tile transposed through shared memory (coalesced on both sides)
@@ -226,6 +262,12 @@ extern "C" int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream) {
     MR_REQUIRE((d.Ho - 1) * d.oy_step + d.oy_off < d.dst_H && (d.Wo - 1) * d.ox_step + d.ox_off < d.dst_W,
                "mr_conv2d_nhwc: output placement out of range");
     MR_REQUIRE(d.act >= MR_ACT_NONE && d.act <= MR_ACT_ABSTANH, "mr_conv2d_nhwc: unknown activation %d", d.act);
+    if (d.Cout == 1 && d.n_src == 1 && !d.upsample2 && (d.src_c[0] % 4) == 0 && d.kh * d.kw * d.src_c[0] * 4 <= 40 * 1024) {
+        const size_t total = (size_t)d.B * d.Ho * d.Wo;
+        conv_cout1_kernel<<<(unsigned)((total + 255) / 256), 256, (size_t)d.kh * d.kw * d.src_c[0] * 4, (cudaStream_t)stream>>>(d);
+        MR_LAUNCH_CHECK("conv_cout1_kernel");
+        return MR_OK;
+    }
     const int tiles = ((d.Ho + kTileH - 1) / kTileH) * ((d.Wo + kTileW - 1) / kTileW);
     // the per-thread float4 weight reads need Cout-tile-aligned rows: TN=64 only when Cout is a multiple of 4
     if (d.Cout >= 64 && d.Cout % 4 == 0) {
