@@ -508,9 +508,12 @@ __global__ void projection_tables_kernel(const float* kf_pose, const float* kf_K
     }
 }
 
+#ifndef MR_CV_TILE_ROWS
+#define MR_CV_TILE_ROWS 16
+#endif
 int pick_tile_rows(int D, int F) {
     const int limit = 227 * 1024;
-    for (int th = 16; th >= 2; th >>= 1)
+    for (int th = MR_CV_TILE_ROWS; th >= 2; th >>= 1)
         if (make_layout(D, th, F).total <= limit) return th;
     return 0;
 }
