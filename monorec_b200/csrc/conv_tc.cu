@@ -19,6 +19,7 @@
 #include "mr_common.cuh"
 #include <cuda.h>
 #include <cstdint>
+#include <cstdlib>
 
 namespace {
 
@@ -31,7 +32,7 @@ struct TcArgs {
     int n_src;
     int chunks[MR_CONV_MAX_SRC];   // 32-channel chunks per source
     int kh, kw, sy, sx, pad_t, pad_l;
-    int Ho, Wo, Cout, n_pad, tiles_x, stages;
+    int Ho, Wo, Cout, n_pad, tiles_x, tiles_per_img, total_tiles, stages;
     uint32_t tmem_cols;
     const float* bias;
     float* dst;
@@ -112,11 +113,18 @@ __device__ __forceinline__ float act_fn(float v, int act, float a, float b) {
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: each CTA loops over output tiles (tile = blockIdx.x, += gridDim.x).  The TMA->MMA shared-memory ring keeps
+// flowing across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the
+// main loop of tile i+1.
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * 8 + 1];   // full[stages], empty[stages], tmem_full
+    __shared__ __align__(8) uint64_t bars[2 * 8 + 4];   // full[8], empty[8], tmem_full[2], tmem_empty[2]
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,17 +132,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
     const uint32_t stage_bytes = kABytes + b_bytes;
     const int stages = a.stages;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]), tfull = smem_u32(&bars[16]);
-
-    const int tile_y = blockIdx.x / a.tiles_x, tile_x = blockIdx.x - tile_y * a.tiles_x;
-    const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
-    const int b = blockIdx.y;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+    const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
     const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
     const int total = a.kh * a.kw * chunks_per_tap;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tfull, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -157,79 +162,270 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;
-            for (int ky = 0; ky < a.kh; ++ky)
-                for (int kx = 0; kx < a.kw; ++kx) {
-                    const int ix0 = ox0 * a.sx - a.pad_l + kx, iy0 = oy0 * a.sy - a.pad_t + ky;
-                    int kbase = 0;
-                    for (int s = 0; s < a.n_src; ++s) {
-                        const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
-                        for (int j = 0; j < a.chunks[s]; ++j, ++it) {
-                            const int st = it % stages;
-                            const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                            mbar_wait(empty0 + 8 * st, ph ^ 1u);
-                            const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
-                            mbar_expect_tx(full0 + 8 * st, stage_bytes);
-                            tma_load_4d(sa, tm, full0 + 8 * st, j * kKC, ix0, iy0, b);
-                            tma_load_2d(sb, &tmB, full0 + 8 * st, kbase + j * kKC, (ky * a.kw + kx) * a.n_pad);
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+                const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+                const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
+                for (int ky = 0; ky < a.kh; ++ky)
+                    for (int kx = 0; kx < a.kw; ++kx) {
+                        const int ix0 = ox0 * a.sx - a.pad_l + kx, iy0 = oy0 * a.sy - a.pad_t + ky;
+                        int kbase = 0;
+                        for (int s = 0; s < a.n_src; ++s) {
+                            const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
+                            for (int j = 0; j < a.chunks[s]; ++j, ++it) {
+                                const int st = it % stages;
+                                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                                mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                                const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
+                                mbar_expect_tx(full0 + 8 * st, stage_bytes);
+                                tma_load_4d(sa, tm, full0 + 8 * st, j * kKC, ix0, iy0, b);
+                                tma_load_2d(sb, &tmB, full0 + 8 * st, kbase + j * kKC, (ky * a.kw + kx) * a.n_pad);
+                            }
+                            kbase += a.chunks[s] * kKC;
                         }
-                        kbase += a.chunks[s] * kKC;
                     }
-                }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6), a/b format TF32 = 2 @[7,10)/[10,13),
         // K-major A and B, N >> 3 @[17,23), M >> 4 @[24,29)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((128u >> 4) << 24);
-        for (int it = 0; it < total; ++it) {
-            const int st = it % stages;
-            const uint32_t ph = (uint32_t)(it / stages) & 1u;
-            mbar_wait(full0 + 8 * st, ph);
+        int it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+            const int buf = lt & 1;
+            mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
-                const uint64_t da = make_desc(sa), db = make_desc(sb);
+            const uint32_t acc = tmem_d + (uint32_t)(buf * a.n_pad);
+            for (int c = 0; c < total; ++c, ++it) {
+                const int st = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                mbar_wait(full0 + 8 * st, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
+                    const uint64_t da = make_desc(sa), db = make_desc(sb);
 #pragma unroll
-                for (int k = 0; k < kKC / 8; ++k)   // UMMA K = 8 for tf32: advance 32 bytes inside the swizzle row
-                    umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
-                umma_commit(empty0 + 8 * st);               // frees the smem stage once these MMAs have read it
-                if (it == total - 1) umma_commit(tfull);    // accumulator complete
+                    for (int k = 0; k < kKC / 8; ++k)   // UMMA K = 8 for tf32: advance 32 bytes inside the swizzle row
+                        umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * st);                      // frees the smem stage once these MMAs have read it
+                    if (c == total - 1) umma_commit(tfull0 + 8 * buf); // accumulator complete
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> bias/activation -> NHWC =====================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int p = 32 * q + lane;            // pixel (= accumulator row) of this thread
-        const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
-        const bool live = (oy < a.Ho) && (ox < a.Wo);
-        float* op = a.dst + (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
-                                a.dst_c + a.dst_coff;
-        mbar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16);
         const bool vec_ok = ((a.dst_c | a.dst_coff) & 3) == 0;
-        for (int n0 = 0; n0 < a.n_pad; n0 += 8) {
-            uint32_t r[8];
-            tmem_ld8(trow + (uint32_t)n0, r);
-            if (!live) continue;
-            float v[8];
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+            const int oy = tile_y * kTileH + (p >> 4), ox = tile_x * kTileW + (p & 15);
+            const bool live = (oy < a.Ho) && (ox < a.Wo);
+            float* op = a.dst + (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+                                    a.dst_c + a.dst_coff;
+            const int buf = lt & 1;
+            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
+            for (int n0 = 0; n0 < a.n_pad; n0 += 8) {
+                uint32_t r[8];
+                tmem_ld8(trow + (uint32_t)n0, r);
+                if (!live) continue;
+                float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int n = n0 + j;
-                float x = __uint_as_float(r[j]) + ((a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
-                x = act_fn(x, a.act, a.act_a, a.act_b);
-                if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-                v[j] = x;
-            }
-            if (vec_ok && n0 + 8 <= a.Cout) {
-                *reinterpret_cast<float4*>(op + n0) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(op + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            } else {
+                for (int j = 0; j < 8; ++j) {
+                    const int n = n0 + j;
+                    float x = __uint_as_float(r[j]) + ((a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
+                    x = act_fn(x, a.act, a.act_a, a.act_b);
+                    if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+                    v[j] = x;
+                }
+                if (vec_ok && n0 + 8 <= a.Cout) {
+                    *reinterpret_cast<float4*>(op + n0) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(op + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (n0 + j < a.Cout) op[n0 + j] = v[j];
+                    for (int j = 0; j < 8; ++j)
+                        if (n0 + j < a.Cout) op[n0 + j] = v[j];
+                }
             }
+            // hand the accumulator buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(a.tmem_cols));
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------------------
+// Stride-1 layers with small weights (the full-resolution 24..64-channel layers that dominate the stacks): "halo" variant.
+//   * the whole packed weight tensor of the layer is loaded into shared memory ONCE per CTA (resident B);
+//   * per (tile, source, 32-channel chunk) ONE TMA box {32 ch, 16 px, 16 + kh - 1 px} brings the input tile with its halo;
+//     every filter tap is then just a different shared-memory descriptor into that box: start address shifted by
+//     (ky * 16 + kx) rows of 128 B, stride between 8-row groups = one halo row (2048 B), swizzle phase carried by the
+//     descriptor's base-offset field.  L2->SM traffic drops from kh*kw boxes per tile to one.
+// Output tile = 16 rows x 8 columns (an 8-row MMA group = 8 adjacent pixels of one output row).
+// -------------------------------------------------------------------------------------------------------------------------
+#ifndef MR_HALO_BASE_OFFSET
+#define MR_HALO_BASE_OFFSET 0
+#endif
+constexpr int kHaloPitch = 16;   // pixels per halo row in smem (8 outputs + up to 8 taps to the right)
+
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr) {
+    // K-major SWIZZLE_128B, SBO = one halo row (16 px * 128 B = 2048 B), base offset = 128-byte row phase of the start
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)(MR_HALO_BASE_OFFSET ? ((saddr >> 7) & 7) : 0) << 49) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * 4 + 4 + 1];   // afull[4], aempty[4], tmem_full[2], tmem_empty[2], bfull
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
+    const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
+    const int taps = a.kh * a.kw;
+    const uint32_t bres_bytes = (uint32_t)(taps * chunks_per_tap) * b_bytes;       // multiple of 1024 (n_pad % 16 == 0 -> % 2048)
+    const uint32_t a_bytes = (uint32_t)(16 + a.kh - 1) * kHaloPitch * 128u;
+    const uint32_t a_base = base + ((bres_bytes + 1023u) & ~1023u);
+    const int stages = a.stages;
+    const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[4]);
+    const uint32_t tfull0 = smem_u32(&bars[8]), tempty0 = smem_u32(&bars[10]), bfull = smem_u32(&bars[12]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+        mbar_init(bfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA0);
+        if (a.n_src > 1) prefetch_tmap(&tmA1);
+        if (a.n_src > 2) prefetch_tmap(&tmA2);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(a.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            // resident weights: every (tap, chunk) slice [n_pad x 32] once
+            mbar_expect_tx(bfull, bres_bytes);
+            for (int tp = 0; tp < taps; ++tp)
+                for (int cg = 0; cg < chunks_per_tap; ++cg)
+                    tma_load_2d(base + (uint32_t)(tp * chunks_per_tap + cg) * b_bytes, &tmB, bfull, cg * kKC, tp * a.n_pad);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+                const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+                const int ix0 = tile_x * 8 - a.pad_l, iy0 = tile_y * 16 - a.pad_t;
+                for (int s = 0; s < a.n_src; ++s) {
+                    const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
+                    for (int j = 0; j < a.chunks[s]; ++j, ++it) {
+                        const int st = it % stages;
+                        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                        mbar_wait(aempty0 + 8 * st, ph ^ 1u);
+                        mbar_expect_tx(afull0 + 8 * st, a_bytes);
+                        tma_load_4d(a_base + st * a_bytes, tm, afull0 + 8 * st, j * kKC, ix0, iy0, b);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+        mbar_wait(bfull, 0);
+        int it = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+            const int buf = lt & 1;
+            mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem_d + (uint32_t)(buf * a.n_pad);
+            for (int cg = 0; cg < chunks_per_tap; ++cg, ++it) {
+                const int st = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+                mbar_wait(afull0 + 8 * st, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t sa = a_base + st * a_bytes;
+                    for (int ky = 0; ky < a.kh; ++ky)
+                        for (int kx = 0; kx < a.kw; ++kx) {
+                            const uint64_t da = make_desc_halo(sa + (uint32_t)(ky * kHaloPitch + kx) * 128u);
+                            const uint64_t db = make_desc(base + (uint32_t)((ky * a.kw + kx) * chunks_per_tap + cg) * b_bytes);
+#pragma unroll
+                            for (int k = 0; k < kKC / 8; ++k)
+                                umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
+                        }
+                    umma_commit(aempty0 + 8 * st);
+                    if (cg == chunks_per_tap - 1) umma_commit(tfull0 + 8 * buf);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue (tile = 16 rows x 8 columns) =====================
+        const int q = warp & 3;
+        const int p = 32 * q + lane;
+        const bool vec_ok = ((a.dst_c | a.dst_coff) & 3) == 0;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+            const int oy = tile_y * 16 + (p >> 3), ox = tile_x * 8 + (p & 7);
+            const bool live = (oy < a.Ho) && (ox < a.Wo);
+            float* op = a.dst + (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+                                    a.dst_c + a.dst_coff;
+            const int buf = lt & 1;
+            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
+            for (int n0 = 0; n0 < a.n_pad; n0 += 8) {
+                uint32_t r[8];
+                tmem_ld8(trow + (uint32_t)n0, r);
+                if (!live) continue;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int n = n0 + j;
+                    float x = __uint_as_float(r[j]) + ((a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
+                    x = act_fn(x, a.act, a.act_a, a.act_b);
+                    if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+                    v[j] = x;
+                }
+                if (vec_ok && n0 + 8 <= a.Cout) {
+                    *reinterpret_cast<float4*>(op + n0) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(op + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (n0 + j < a.Cout) op[n0 + j] = v[j];
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -280,6 +476,13 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     TcArgs a{};
     a.n_src = d.n_src;
     int ksum = 0;
+    // "halo" variant (one input box per tile, resident weights): stride 1, taps reach at most 8 px to the right, weights fit
+    int chunks_all = 0;
+    for (int s = 0; s < d.n_src; ++s) chunks_all += (d.src_c[s] + kKC - 1) / kKC;
+    const size_t bres = (size_t)d.kh * d.kw * chunks_all * n_pad * 128;
+    static const bool halo_enabled = (getenv("MONOREC_B200_TC_HALO") != nullptr) && (atoi(getenv("MONOREC_B200_TC_HALO")) != 0);  // experimental, off by default
+    const bool halo = halo_enabled && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7 && bres <= 112 * 1024 &&
+                      (210 * 1024 - ((bres + 1023) & ~size_t(1023))) / ((size_t)(16 + d.kh - 1) * kHaloPitch * 128) >= 2;
     CUtensorMap tmA[MR_CONV_MAX_SRC];
     for (int s = 0; s < d.n_src; ++s) {
         const int C = d.src_c[s];
@@ -291,7 +494,8 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)d.Ws, (cuuint64_t)d.Hs, (cuuint64_t)d.B};
         const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)d.Ws * C * 4, (cuuint64_t)d.Hs * d.Ws * C * 4};
         // with a traversal stride s the box spans box/s loaded elements: 16 (8) output pixels need a span of 16*s (8*s)
-        const cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)(kTileW * d.sx), (cuuint32_t)(kTileH * d.sy), 1};
+        cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)(kTileW * d.sx), (cuuint32_t)(kTileH * d.sy), 1};
+        if (halo) { box[1] = kHaloPitch; box[2] = (cuuint32_t)(16 + d.kh - 1); }
         const cuuint32_t estr[4] = {1, (cuuint32_t)d.sx, (cuuint32_t)d.sy, 1};
         CUresult r = encode(&tmA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.src[s]), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -320,27 +524,49 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     }
     a.kh = d.kh; a.kw = d.kw; a.sy = d.sy; a.sx = d.sx; a.pad_t = d.pad_t; a.pad_l = d.pad_l;
     a.Ho = d.Ho; a.Wo = d.Wo; a.Cout = d.Cout; a.n_pad = n_pad;
-    a.tiles_x = (d.Wo + kTileW - 1) / kTileW;
-    const int tiles = a.tiles_x * ((d.Ho + kTileH - 1) / kTileH);
-    const int total = d.kh * d.kw * (a.chunks[0] + a.chunks[1] + a.chunks[2]);
+    a.tiles_x = halo ? (d.Wo + 7) / 8 : (d.Wo + kTileW - 1) / kTileW;
+    const int tiles = a.tiles_x * (halo ? (d.Ho + 15) / 16 : (d.Ho + kTileH - 1) / kTileH);
     const size_t stage_bytes = (size_t)kABytes + (size_t)n_pad * 128;
-    // several CTAs per SM overlap one tile's epilogue with another tile's main loop (non-persistent kernel): keep the
-    // ring at ~72 KB so that three CTAs (two for the widest layers) are resident
-    int stages = (int)((72 * 1024) / stage_bytes);
-    if (stages > 4) stages = 4;
+    a.tiles_per_img = tiles;
+    a.total_tiles = tiles * d.B;
+    // persistent grid: two CTAs per SM when two double-buffered accumulators fit TMEM (2 x 2 x n_pad <= 512 columns),
+    // otherwise one CTA per SM with a deeper ring
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ctas_per_sm = (n_pad <= 128) ? 2 : 1;
+    const size_t budget = (ctas_per_sm == 2) ? 100 * 1024 : 200 * 1024;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
-    if (stages > total) stages = total;
     a.stages = stages;
     uint32_t cols = 32;
-    while (cols < (uint32_t)n_pad) cols <<= 1;
+    while (cols < (uint32_t)(2 * n_pad)) cols <<= 1;
     a.tmem_cols = cols;
     a.bias = d.bias; a.dst = d.dst;
     a.dst_H = d.dst_H; a.dst_W = d.dst_W; a.dst_c = d.dst_c; a.dst_coff = d.dst_coff;
     a.oy_step = d.oy_step; a.ox_step = d.ox_step; a.oy_off = d.oy_off; a.ox_off = d.ox_off;
     a.act = d.act; a.act_a = d.act_a; a.act_b = d.act_b; a.round_out = round_out;
+    if (halo) {
+        const size_t a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * 128;
+        const size_t bres_al = (bres + 1023) & ~size_t(1023);
+        int st = (int)((210 * 1024 - bres_al) / a_bytes);
+        if (st > 4) st = 4;
+        if (st >= 2) {
+            a.stages = st;
+            const size_t smem = bres_al + (size_t)st * a_bytes + 1024;
+            MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+            int grid = sms;
+            if (grid > a.total_tiles) grid = a.total_tiles;
+            conv_tc_halo_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+            MR_LAUNCH_CHECK("conv_tc_halo_kernel");
+            return MR_OK;
+        }
+    }
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    dim3 grid(tiles, d.B);
+    int grid = sms * ctas_per_sm;
+    if (grid > a.total_tiles) grid = a.total_tiles;
     conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
     MR_LAUNCH_CHECK("conv_tc_kernel");
     return MR_OK;

@@ -1,0 +1,43 @@
+"""Times representative conv layers of the stacks on the tensor-core path (CUDA events), halo variant on/off via env."""
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from monorec_b200 import conv as C  # noqa: E402
+
+C.set_mode("tf32")
+dev = "cuda:0"
+torch.manual_seed(0)
+
+
+def timed(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+cases = [("mask enc0 3x3 32->32 B32 full", 32, 256, 512, (32,), 32, 3, 3),
+         ("depth enc0 7x1 36->48 B8 full", 8, 256, 512, (36,), 48, 7, 1),
+         ("depth enc0 1x7 48->48 B8 full", 8, 256, 512, (48,), 48, 1, 7),
+         ("mask dec3.2 3x3 48->48 B8 full", 8, 256, 512, (48,), 48, 3, 3),
+         ("mask dec3.1 3x3 32+64->48 B8 full", 8, 256, 512, (32, 64), 48, 3, 3),
+         ("mask enc1 3x3 48->48 B32 half", 32, 128, 256, (48,), 48, 3, 3),
+         ("mask dec1.1 3x3 64+64+96->96 B8 1/4", 8, 64, 128, (64, 64, 96), 96, 3, 3)]
+for name, B, H, W, src_c, cout, kh, kw in cases:
+    xs = [torch.randn(B, H, W, c, device=dev) for c in src_c]
+    conv = torch.nn.Conv2d(sum(src_c), cout, (kh, kw)).to(dev)
+    L = C.PackedConv(conv.weight, conv.bias, src_c, act=C.ACT_LEAKY, act_a=0.1)
+    us = timed(lambda: L(xs))
+    flops = 2.0 * B * H * W * sum(src_c) * cout * kh * kw
+    byts = 4.0 * B * H * W * (sum(src_c) + cout)
+    print(f"{name:40s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {byts / us / 1e3:7.1f} GB/s (in+out)")
