@@ -156,3 +156,36 @@ def test_error_behaviour():
         _run(data)   # F = 9 > MR_MAX_FRAMES
     with pytest.raises(KeyError):
         CostVolumeModule()({"keyframe": torch.zeros(1, 3, 32, 64, device="cuda:0")})
+
+
+@pytest.mark.parametrize("cfg", [(1, 2, 32, 37, 61, 31), (2, 1, 8, 48, 333, 32), (1, 3, 32, 100, 500, 33), (1, 2, 128, 32, 64, 34),
+                                 (1, 8, 4, 24, 70, 35)])
+def test_ragged_shapes_against_oracle(cfg):
+    """tile edges: W not a multiple of the 60-column tile (and odd: scalar stores), H not a multiple of 16, D from 4 to 128,
+    F from 1 to MR_MAX_FRAMES"""
+    from oracle import cost_volume_oracle as O
+    from monorec_b200.synthetic import make_inputs
+    B, F, D, H, W, seed = cfg
+    data = make_inputs(B, F, H, W, seed=seed)
+    ref_cv, ref_sf = O.cost_volume_torch(data, steps=D)
+    cv, sf = _run(data, steps=D)
+    print(cfg, compare_volumes(cv, sf, ref_cv, ref_sf))
+
+
+def test_hires_config_small_batch():
+    """BASELINE config 5 shape (512x1024, D=64, F=6) on one keyframe: properties only (the CPU oracle needs 42 GB here)"""
+    from monorec_b200.synthetic import make_inputs
+    data = make_inputs(1, 6, 512, 1024, seed=40)
+    cv, sf = _run(data, steps=64)
+    assert cv.shape == (1, 64, 512, 1024) and len(sf) == 6
+    assert torch.isfinite(cv).all() and cv.abs().max() <= 1.0 + 1e-6
+    for t in [cv] + sf:
+        assert (t[..., :2, :] == 0).all() and (t[..., -2:, :] == 0).all() and (t[..., :, :2] == 0).all() and (t[..., :, -2:] == 0).all()
+    # frame order must not matter for the single-frame volumes at this size either
+    perm = [5, 3, 1, 0, 2, 4]
+    pd = dict(data)
+    for k in ("frames", "poses", "intrinsics"):
+        pd[k] = [data[k][i] for i in perm]
+    cvp, sfp = _run(pd, steps=64)
+    assert all(torch.equal(sfp[j], sf[perm[j]]) for j in range(6))
+    assert (cvp - cv).abs().max() <= 1e-5
