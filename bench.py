@@ -33,6 +33,14 @@ METRIC = "keyframes_per_s_256x512_D32_F4"
 ALG_BYTES_PER_KEYFRAME = 4 * H * W * (1 + F) * (3 + D)   # every input read once, every output written once
 
 
+def k1_traffic():
+    """DRAM bytes per launch of the cost-volume kernel from the committed `ncu --set full` capture (config 2)."""
+    p = ROOT / "profiles" / "r01_k1_traffic.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["traffic_bytes_per_launch"])
+    return None
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -230,7 +238,7 @@ def main():
                            "l2": f"inputs rotate over {NSETS} sets (252 MB) > 126 MB L2; 671 MB of outputs per step"},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": f"{peak_src} (burst copy)",
+                             "frac": achieved / peak, "traffic": k1_traffic(), "peak_source": f"{peak_src} (burst copy)",
                              "kernel": "cost_volume_kernel", "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_KEYFRAME * B},
                 "clocks": clocks.summary()}

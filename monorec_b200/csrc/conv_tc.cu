@@ -97,12 +97,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float act_fn(float v, int act, float a, float b) {
     switch (act) {
@@ -110,6 +112,42 @@ __device__ __forceinline__ float act_fn(float v, int act, float a, float b) {
         case MR_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
         case MR_ACT_ABSTANH: return fmaf(b, fabsf(tanhf(v)), a);
         default: return v;
+    }
+}
+
+// Epilogue of one accumulator row (= one output pixel): 32 columns per step (two x16 TMEM loads, one wait), bias from shared
+// memory, activation, optional TF32 rounding, 16-byte NHWC stores.
+__device__ __forceinline__ void epilogue_row(uint32_t trow, const TcArgs& a, const float* bias_s, float* op, bool live,
+                                             bool vec_ok) {
+    for (int n0 = 0; n0 < a.n_pad; n0 += 32) {
+        uint32_t r0[16], r1[16];
+        const bool second = n0 + 16 < a.n_pad;
+        tmem_ld16_nowait(trow + (uint32_t)n0, r0);
+        if (second) tmem_ld16_nowait(trow + (uint32_t)(n0 + 16), r1);
+        tmem_ld_wait();
+        if (!live) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !second) break;
+            const int nb = n0 + 16 * h;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(h ? r1[j] : r0[j]) + bias_s[nb + j];
+                if (a.act == MR_ACT_LEAKY) x = fmaxf(x, a.act_a * x);          // slope in (0, 1)
+                else if (a.act != MR_ACT_NONE) x = act_fn(x, a.act, a.act_a, a.act_b);
+                if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+                v[j] = x;
+            }
+            if (vec_ok && nb + 16 <= a.Cout) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (nb + j < a.Cout) op[nb + j] = v[j];
+            }
+        }
     }
 }
 
@@ -126,6 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * 8 + 4];   // full[8], empty[8], tmem_full[2], tmem_empty[2]
     __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -142,6 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < 256; i += kTcThreads) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA0);
         if (a.n_src > 1) prefetch_tmap(&tmA1);
@@ -231,28 +271,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            for (int n0 = 0; n0 < a.n_pad; n0 += 8) {
-                uint32_t r[8];
-                tmem_ld8(trow + (uint32_t)n0, r);
-                if (!live) continue;
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = n0 + j;
-                    float x = __uint_as_float(r[j]) + ((a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
-                    x = act_fn(x, a.act, a.act_a, a.act_b);
-                    if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-                    v[j] = x;
-                }
-                if (vec_ok && n0 + 8 <= a.Cout) {
-                    *reinterpret_cast<float4*>(op + n0) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(op + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (n0 + j < a.Cout) op[n0 + j] = v[j];
-                }
-            }
+            epilogue_row(trow, a, bias_s, op, live, vec_ok);
             // hand the accumulator buffer back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -293,6 +312,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * 4 + 4 + 1];   // afull[4], aempty[4], tmem_full[2], tmem_empty[2], bfull
     __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -312,6 +332,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < 256; i += kTcThreads) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA0);
         if (a.n_src > 1) prefetch_tmap(&tmA1);
@@ -401,28 +422,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            for (int n0 = 0; n0 < a.n_pad; n0 += 8) {
-                uint32_t r[8];
-                tmem_ld8(trow + (uint32_t)n0, r);
-                if (!live) continue;
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int n = n0 + j;
-                    float x = __uint_as_float(r[j]) + ((a.bias != nullptr && n < a.Cout) ? __ldg(a.bias + n) : 0.f);
-                    x = act_fn(x, a.act, a.act_a, a.act_b);
-                    if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-                    v[j] = x;
-                }
-                if (vec_ok && n0 + 8 <= a.Cout) {
-                    *reinterpret_cast<float4*>(op + n0) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(op + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (n0 + j < a.Cout) op[n0 + j] = v[j];
-                }
-            }
+            epilogue_row(trow, a, bias_s, op, live, vec_ok);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);

@@ -251,3 +251,15 @@ def test_modules_tf32_vs_oracle(tf32_mode):
     ed = [_rel(p.cpu(), r) for p, r in zip(d["predicted_inverse_depths"], ref_depth)]
     print("tf32 stacks: mask rel err", em, "depth rel err", ed)
     assert em < 1e-2 and max(ed) < 1e-2
+
+
+def test_tc_halo_variant_in_subprocess():
+    """The opt-in halo-reuse kernel (MONOREC_B200_TC_HALO=1; one input box per tile, resident weights) computes the same
+    layers; the switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, MONOREC_B200_TC_HALO="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "tc_conv_matches_torch or tc_concat"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
