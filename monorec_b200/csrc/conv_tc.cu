@@ -534,8 +534,15 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ctas_per_sm = (n_pad <= 128) ? 2 : 1;
-    const size_t budget = (ctas_per_sm == 2) ? 100 * 1024 : 200 * 1024;
+    static const int kForceCtas = getenv("MONOREC_B200_TC_CTAS") ? atoi(getenv("MONOREC_B200_TC_CTAS")) : 0;   // tuning knob
+    // resident CTAs per SM: bounded by TMEM (each CTA holds a power-of-two >= 2 * n_pad columns of the 512) and capped at 4;
+    // with UMMA N = 32..64 one CTA cannot keep the tensor pipe busy, so several CTAs interleave their MMA chains
+    uint32_t cols_needed = 32;
+    while (cols_needed < (uint32_t)(2 * n_pad)) cols_needed <<= 1;
+    int ctas_per_sm = (int)(512 / cols_needed);
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    if (kForceCtas > 0 && (uint32_t)kForceCtas * cols_needed <= 512) ctas_per_sm = kForceCtas;
+    const size_t budget = (size_t)(200 * 1024) / ctas_per_sm;
     int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;

@@ -86,11 +86,17 @@ class ResnetEncoder(nn.Module):
         if num_layers != 18:
             raise NotImplementedError("monorec_b200: the reference only ever instantiates ResnetEncoder(18)")
         self.num_ch_enc = np.array([64, 64, 128, 256, 512])
-        try:
-            weights = torchvision.models.ResNet18_Weights.IMAGENET1K_V1 if pretrained else None
-            self.encoder = torchvision.models.resnet18(weights=weights)
-        except Exception:  # offline: ImageNet weights cannot be downloaded; a checkpoint is expected to supply them
-            self.encoder = torchvision.models.resnet18(weights=None)
+        # The reference asks torchvision for ImageNet weights (:104-113).  They are used only if already in the local hub
+        # cache: a MonoRec checkpoint carries `_feature_extractor.encoder.*` anyway, and this code must stay silent and
+        # offline-safe (no download attempt, nothing printed to stdout).
+        weights = None
+        if pretrained:
+            import os
+            w = torchvision.models.ResNet18_Weights.IMAGENET1K_V1
+            cached = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
+            if os.path.isfile(cached):
+                weights = w
+        self.encoder = torchvision.models.resnet18(weights=weights)
 
     def forward(self, input_image):
         e = self.encoder
