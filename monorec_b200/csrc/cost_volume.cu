@@ -84,6 +84,25 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return r;
 }
 
+// L2 residency hints: the single-frame volume is written by the march and read back once by the per-pixel phase of the same
+// CTA, so its lines are asked to stay (evict_last); the fused volume is written once and never read here (evict_first).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint_f2(float* ptr, float2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(ptr), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_f1(float* ptr, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 constexpr int kChunk = 32;                 // planes the per-pixel phase keeps in registers at once
@@ -169,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
     const bool st0 = (lane >= 1) && (lane <= 30) && (ucol < W);
     const bool st1 = (lane >= 1) && (lane <= 30) && (ucol + 1 < W);
     const bool st_pair = st0 && st1 && ((W & 1) == 0);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
     // ---- validity pre-pass for every frame: valid_f(v,u) = interior(v,u) & all_d [ sample strictly inside
     //      (1,W-2)x(1,H-2) ]  (monorec_model.py:212-219: bilinear sample of the interior mask != 0 for every plane) ----
@@ -348,10 +368,10 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
                     float* o = out_d + (size_t)(r - 2) * W;
                     if (v0 + r - 2 < H) {
                         if (st_pair) {
-                            *reinterpret_cast<float2*>(o) = sv;
+                            st_hint_f2(o, sv, pol_keep);
                         } else {
-                            if (st0) o[0] = sv.x;
-                            if (st1) o[1] = sv.y;
+                            if (st0) st_hint_f1(o, sv.x, pol_keep);
+                            if (st1) st_hint_f1(o + 1, sv.y, pol_keep);
                         }
                     }
                 }
@@ -426,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
             const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
 #pragma unroll
             for (int j = 0; j < kChunk; ++j)
-                if (d0 + j < D) cv_out[(size_t)(d0 + j) * plane] = (wsum == 0.f) ? 0.f : acc[j] * inv;
+                if (d0 + j < D) st_hint_f1(cv_out + (size_t)(d0 + j) * plane, (wsum == 0.f) ? 0.f : acc[j] * inv, pol_stream);
         }
     }
 }
