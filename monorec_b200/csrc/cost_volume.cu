@@ -121,6 +121,185 @@ __device__ __forceinline__ void ssim_nd(float2 s1, float2 sxx, float2 sxy, float
     d = mul2(add2(mxx, fma2(mu_y, mu_y, bc2(kC1))), add2(sig_x, sy2));
 }
 
+// ---- stage 1 of the march: homography of one tile row (pair = columns lane, lane + 32) and its 24 bilinear taps -------
+struct Stage1Ctx {
+    float2 pzx, pzy, pzz;             // per-lane column part of the projection (already times the plane depth)
+    float rax, rbx, ray, rby, raz, rbz;  // per-row part: c = pz(u) + ra * v + rb
+    const float* img;                 // source frame of this batch element, [3][H][W]
+    int W, H, planei, v0, lane;
+    float sx_lo, sx_hi, sy_lo, sy_hi; // == grid clamp(-2, 2), monorec_model.py:208
+};
+
+__device__ __forceinline__ void setup_stage1(Stage1Ctx& c, const float* m, const float* img, float z, float2 fu2) {
+    // projection c = M [u v 1]^T z + p split into a per-lane column part and a per-row part
+    c.pzx = mul2(mul2(bc2(m[0]), fu2), bc2(z));
+    c.pzy = mul2(mul2(bc2(m[4]), fu2), bc2(z));
+    c.pzz = mul2(mul2(bc2(m[8]), fu2), bc2(z));
+    c.rax = m[1] * z; c.rbx = fmaf(m[2], z, m[3]);
+    c.ray = m[5] * z; c.rby = fmaf(m[6], z, m[7]);
+    c.raz = m[9] * z; c.rbz = fmaf(m[10], z, m[11]);
+    c.img = img;
+}
+
+__device__ __forceinline__ void warp_row(const Stage1Ctx& c, const int r, float* __restrict__ xrow) {
+    const int W = c.W, H = c.H;
+    const float fv = (float)(c.v0 + r);
+    const float rcx = fmaf(c.rax, fv, c.rbx), rcy = fmaf(c.ray, fv, c.rby), rcz = fmaf(c.raz, fv, c.rbz);
+    const float2 cx = add2(c.pzx, bc2(rcx)), cy = add2(c.pzy, bc2(rcy)), cz = add2(c.pzz, bc2(rcz));
+    const float2 inv = make_float2(fast_rcp(cz.x), fast_rcp(cz.y));
+    const float2 ux = mul2(cx, inv), uy = mul2(cy, inv);
+    // floor by magic-number rounding: rn(s - 0.5) differs from floor(s) only for integral s, where the interpolated value
+    // is the same (weight 1 on the tap both conventions share)
+    const float2 tx = add2(ux, bc2(kMagic - 1.0f)), ty = add2(uy, bc2(kMagic - 1.0f));
+    const int x0a = __float_as_int(tx.x) - kMagicBits, x0b = __float_as_int(tx.y) - kMagicBits;
+    const int y0a = __float_as_int(ty.x) - kMagicBits, y0b = __float_as_int(ty.y) - kMagicBits;
+    const bool inb = ((unsigned)x0a <= (unsigned)(W - 2)) && ((unsigned)x0b <= (unsigned)(W - 2)) &&
+                     ((unsigned)y0a <= (unsigned)(H - 2)) && ((unsigned)y0b <= (unsigned)(H - 2));
+    float2 w00, w01, w10, w11;
+    int oa, ob, dxa, dxb, dya, dyb;
+    if (__all_sync(0xffffffffu, inb)) {
+        // fast path: all 4 taps of every lane are inside the image
+        const float2 x0f = add2(tx, bc2(-kMagic)), y0f = add2(ty, bc2(-kMagic));
+        const float2 wx1 = add2(add2(ux, bc2(-0.5f)), neg2(x0f)), wy1 = add2(add2(uy, bc2(-0.5f)), neg2(y0f));
+        const float2 wx0 = add2(bc2(1.0f), neg2(wx1)), wy0 = add2(bc2(1.0f), neg2(wy1));
+        w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
+        oa = y0a * W + x0a; ob = y0b * W + x0b;
+        dxa = dxb = 1; dya = dyb = W;
+    } else {
+        // border path: per-tap zero padding exactly like F.grid_sample(padding_mode="zeros"): clamp the tap address, zero
+        // the weight of every tap that falls outside the image
+        float wx0s[2], wx1s[2], wy0s[2], wy1s[2];
+        int os[2], dxs[2], dys[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            float sxk = (k ? ux.y : ux.x) - 0.5f, syk = (k ? uy.y : uy.x) - 0.5f;
+            sxk = fminf(fmaxf(sxk, c.sx_lo), c.sx_hi);
+            syk = fminf(fmaxf(syk, c.sy_lo), c.sy_hi);
+            const float x0f = floorf(sxk), y0f = floorf(syk);
+            float wx1 = sxk - x0f, wy1 = syk - y0f;
+            float wx0 = (x0f + 1.0f) - sxk, wy0 = (y0f + 1.0f) - syk;
+            const int x0 = (int)x0f, y0 = (int)y0f;
+            if ((unsigned)x0 >= (unsigned)W) wx0 = 0.f;
+            if ((unsigned)(x0 + 1) >= (unsigned)W) wx1 = 0.f;
+            if ((unsigned)y0 >= (unsigned)H) wy0 = 0.f;
+            if ((unsigned)(y0 + 1) >= (unsigned)H) wy1 = 0.f;
+            const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+            const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
+            wx0s[k] = wx0; wx1s[k] = wx1; wy0s[k] = wy0; wy1s[k] = wy1;
+            os[k] = ya * W + xa; dxs[k] = xb - xa; dys[k] = (yb - ya) * W;
+        }
+        const float2 wx0 = make_float2(wx0s[0], wx0s[1]), wx1 = make_float2(wx1s[0], wx1s[1]);
+        const float2 wy0 = make_float2(wy0s[0], wy0s[1]), wy1 = make_float2(wy1s[0], wy1s[1]);
+        w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
+        oa = os[0]; ob = os[1]; dxa = dxs[0]; dxb = dxs[1]; dya = dys[0]; dyb = dys[1];
+    }
+    // the source row the next row step will newly touch: bring its lines into L1 now (no registers held)
+    const int pfa = min(oa + 2 * W, c.planei - 1), pfb = min(ob + 2 * W, c.planei - 1);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float* pa0 = c.img + (oa + ch * c.planei);
+        const float* pb0 = c.img + (ob + ch * c.planei);
+        const float* pa1 = pa0 + dya;
+        const float* pb1 = pb0 + dyb;
+        const float2 i00 = make_float2(__ldg(pa0), __ldg(pb0));
+        const float2 i01 = make_float2(__ldg(pa0 + dxa), __ldg(pb0 + dxb));
+        const float2 i10 = make_float2(__ldg(pa1), __ldg(pb1));
+        const float2 i11 = make_float2(__ldg(pa1 + dxa), __ldg(pb1 + dxb));
+        prefetch_l1(c.img + (pfa + ch * c.planei));
+        prefetch_l1(c.img + (pfb + ch * c.planei));
+        float2 val = fma2(i00, w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
+        val = fma2(i01, w01, val);
+        val = fma2(i10, w10, val);
+        val = fma2(i11, w11, val);
+        xrow[ch * kRowStride + c.lane + 1] = val.x;
+        xrow[ch * kRowStride + c.lane + 33] = val.y;
+    }
+}
+
+// ---- stage 2 of the march: SSIM + patch cost of one row; lane owns buffer columns 2l, 2l+1 (a pair) ---------------------
+struct Stage2Ctx {
+    const float* ys_l;       // keyframe tile (+0.5), this lane's columns
+    const float4* cs_l;      // hoisted (mu_y, sigma_y + C2) table, this lane's column pair
+    int ych, cch;            // channel strides of the two tables
+    float2 cw0, cw1, cw2;    // channel weights / 9
+    float* out_d;            // single-frame volume plane, tile row 0, this lane's columns
+    int W, rows_left;        // rows_left = H - v0
+    bool st_pair, st0, st1;
+    uint64_t pol_keep;
+};
+
+// rolling state: horizontal 3-sums of X, X^2, XY per channel for the last rows, indexed by (row step mod 3) so that no
+// register moves are needed
+struct Stage2State {
+    float2 hs1[3][3], hsx[3][3], hsy[3][3], hE[3];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            hE[i] = bc2(0.f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) hs1[i][c] = hsx[i][c] = hsy[i][c] = bc2(0.f);
+        }
+    }
+};
+
+template <int P>
+__device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, const int t, const int r,
+                                         const float* __restrict__ xs_l) {
+    constexpr int P1 = (P + 1) % 3, P2 = (P + 2) % 3;
+    const float* yrow = c.ys_l + (r + 2) * kRowStride;
+    float2 nn[3], dd[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float2 xl = *reinterpret_cast<const float2*>(xs_l + ch * kRowStride);      // cols 2l-1, 2l
+        const float2 xr = *reinterpret_cast<const float2*>(xs_l + ch * kRowStride + 2);  // cols 2l+1, 2l+2
+        const float2 yl = *reinterpret_cast<const float2*>(yrow + ch * c.ych);
+        const float2 yr = *reinterpret_cast<const float2*>(yrow + ch * c.ych + 2);
+        const float2 xxl = mul2(xl, xl), xxr = mul2(xr, xr), xyl = mul2(xl, yl), xyr = mul2(xr, yr);
+        const float m1 = xl.y + xr.x, mx = xxl.y + xxr.x, my = xyl.y + xyr.x;
+        const float2 h1 = make_float2(xl.x + m1, m1 + xr.y);
+        const float2 hx = make_float2(xxl.x + mx, mx + xxr.y);
+        const float2 hy = make_float2(xyl.x + my, my + xyr.y);
+        if (t >= 2) {
+            const float4 k4 = c.cs_l[ch * c.cch + r * (kTileCols / 2)];
+            ssim_nd(add2(add2(st.hs1[P1][ch], st.hs1[P2][ch]), h1), add2(add2(st.hsx[P1][ch], st.hsx[P2][ch]), hx),
+                    add2(add2(st.hsy[P1][ch], st.hsy[P2][ch]), hy), make_float2(k4.x, k4.y), make_float2(k4.z, k4.w),
+                    nn[ch], dd[ch]);
+        }
+        st.hs1[P][ch] = h1; st.hsx[P][ch] = hx; st.hsy[P][ch] = hy;
+    }
+    if (t >= 2) {
+        const float2 q0 = mul2(nn[0], make_float2(fast_rcp(dd[0].x), fast_rcp(dd[0].y)));
+        const float2 q1 = mul2(nn[1], make_float2(fast_rcp(dd[1].x), fast_rcp(dd[1].y)));
+        const float2 q2 = mul2(nn[2], make_float2(fast_rcp(dd[2].x), fast_rcp(dd[2].y)));
+        // clamp((1 - q) / 2, 0, 1)   (layers.py:137)
+        const float2 e0 = make_float2(__saturatef(fmaf(-0.5f, q0.x, 0.5f)), __saturatef(fmaf(-0.5f, q0.y, 0.5f)));
+        const float2 e1 = make_float2(__saturatef(fmaf(-0.5f, q1.x, 0.5f)), __saturatef(fmaf(-0.5f, q1.y, 0.5f)));
+        const float2 e2 = make_float2(__saturatef(fmaf(-0.5f, q2.x, 0.5f)), __saturatef(fmaf(-0.5f, q2.y, 0.5f)));
+        const float2 E = fma2(c.cw2, e2, fma2(c.cw1, e1, mul2(c.cw0, e0)));
+        const float eL = __shfl_up_sync(0xffffffffu, E.y, 1);
+        const float eR = __shfl_down_sync(0xffffffffu, E.x, 1);
+        const float mid = E.x + E.y;
+        const float2 hEc = make_float2(eL + mid, mid + eR);
+        if (t >= 4) {
+            // single-frame volume 1 - 2 sad (monorec_model.py:251) straight to HBM; the validity mask is applied by the
+            // per-pixel phase (which zeroes invalid pixels) once all planes are known
+            const float2 sad = add2(add2(st.hE[P1], st.hE[P2]), hEc);
+            const float2 sv = fma2(bc2(-2.0f), sad, bc2(1.0f));
+            float* o = c.out_d + (size_t)(r - 2) * c.W;
+            if (r - 2 < c.rows_left) {
+                if (c.st_pair) {
+                    st_hint_f2(o, sv, c.pol_keep);
+                } else {
+                    if (c.st0) st_hint_f1(o, sv.x, c.pol_keep);
+                    if (c.st1) st_hint_f1(o + 1, sv.y, c.pol_keep);
+                }
+            }
+        }
+        st.hE[P] = hEc;
+    }
+}
+
+
 __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(const CvArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = make_layout(a.D, a.TH, a.F);
@@ -178,7 +357,6 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
     const float2 fu2 = make_float2((float)(u0 + lane), (float)(u0 + lane + 32));
     const float2 cw0 = bc2(a.cw0), cw1 = bc2(a.cw1), cw2 = bc2(a.cw2);
     // per-lane smem bases for stage 2 (columns 2l-1 .. 2l+2 live at float index 2l .. 2l+3 of a row)
-    const float* xs_l = xbuf + 2 * lane;
     const float* ys_l = ytile + 2 * lane;
     const float4* cs_l = reinterpret_cast<const float4*>(cst) + lane;
     const int ych = (TH + 4) * kRowStride;        // ytile channel stride (floats)
@@ -220,174 +398,37 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
     }
     __syncthreads();
 
-    // ---- march: the F*D (frame, plane) units are dealt round-robin to the warps; no CTA-wide barrier in here --------
+    // ---- march over the F*D (frame, plane) units; no CTA-wide barrier in here ------------------------------------
+    Stage2Ctx c2;
+    c2.ys_l = ys_l; c2.cs_l = cs_l; c2.ych = ych; c2.cch = cch;
+    c2.cw0 = cw0; c2.cw1 = cw1; c2.cw2 = cw2;
+    c2.W = W; c2.rows_left = H - v0; c2.st_pair = st_pair; c2.st0 = st0; c2.st1 = st1; c2.pol_keep = pol_keep;
+    Stage1Ctx c1;
+    c1.W = W; c1.H = H; c1.planei = planei; c1.v0 = v0; c1.lane = lane;
+    c1.sx_lo = sx_lo; c1.sx_hi = sx_hi; c1.sy_lo = sy_lo; c1.sy_hi = sy_hi;
     for (int unit = warp; unit < F * D; unit += kWarps) {
         const int f = unit / D, d = unit - f * D;
         const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
-        if (rhi < rlo) continue;  // no valid pixel of this tile for frame f: phase 2 zero-fills
-        const float* m = pjs + 12 * f;
-        const float* img = a.frames[f] + (size_t)b * 3 * plane;
-        const float z = zs[d];
+        if (rhi < rlo) continue;  // no valid pixel of this tile for frame f: the per-pixel phase zero-fills
+        setup_stage1(c1, pjs + 12 * f, a.frames[f] + (size_t)b * 3 * plane, zs[d], fu2);
+        Stage2State st;
+        st.clear();
+        c2.out_d = a.sfcv + (((size_t)f * a.B + b) * D + d) * plane + (size_t)v0 * W + ucol;
         const int nsteps = rhi - rlo + 5;
-        // projection c = M [u v 1]^T z + p split into a per-lane column part and a per-row part
-        const float2 pzx = mul2(mul2(bc2(m[0]), fu2), bc2(z)), pzy = mul2(mul2(bc2(m[4]), fu2), bc2(z)),
-                     pzz = mul2(mul2(bc2(m[8]), fu2), bc2(z));
-        const float rax = m[1] * z, rbx = fmaf(m[2], z, m[3]);
-        const float ray = m[5] * z, rby = fmaf(m[6], z, m[7]);
-        const float raz = m[9] * z, rbz = fmaf(m[10], z, m[11]);
-        // rolling state: horizontal 3-sums of X, X^2, XY per channel (pair = columns 2l, 2l+1) for the last rows,
-        // indexed by (row step mod 3) so that no register moves are needed
-        float2 hs1[3][3], hsx[3][3], hsy[3][3], hE[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            hE[i] = bc2(0.f);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) hs1[i][c] = hsx[i][c] = hsy[i][c] = bc2(0.f);
-        }
-        float* out_d = a.sfcv + (((size_t)f * a.B + b) * D + d) * plane + (size_t)v0 * W + ucol;
-
-        auto row_step = [&](auto phase_tag, const int t) {
-            constexpr int P = decltype(phase_tag)::value;
-            constexpr int P1 = (P + 1) % 3, P2 = (P + 2) % 3;
-            const int r = rlo - 2 + t;  // tile-relative row of the warped row produced in this step
-            // ---------- stage 1: homography of the row (pair = columns lane, lane + 32), 24 bilinear taps ----------
-            {
-                const float fv = (float)(v0 + r);
-                const float rcx = fmaf(rax, fv, rbx), rcy = fmaf(ray, fv, rby), rcz = fmaf(raz, fv, rbz);
-                const float2 cx = add2(pzx, bc2(rcx)), cy = add2(pzy, bc2(rcy)), cz = add2(pzz, bc2(rcz));
-                const float2 inv = make_float2(fast_rcp(cz.x), fast_rcp(cz.y));
-                const float2 ux = mul2(cx, inv), uy = mul2(cy, inv);
-                // floor by magic-number rounding: rn(s - 0.5) differs from floor(s) only for integral s, where the
-                // interpolated value is the same (weight 1 on the tap both conventions share)
-                const float2 tx = add2(ux, bc2(kMagic - 1.0f)), ty = add2(uy, bc2(kMagic - 1.0f));
-                const int x0a = __float_as_int(tx.x) - kMagicBits, x0b = __float_as_int(tx.y) - kMagicBits;
-                const int y0a = __float_as_int(ty.x) - kMagicBits, y0b = __float_as_int(ty.y) - kMagicBits;
-                const bool inb = ((unsigned)x0a <= (unsigned)(W - 2)) && ((unsigned)x0b <= (unsigned)(W - 2)) &&
-                                 ((unsigned)y0a <= (unsigned)(H - 2)) && ((unsigned)y0b <= (unsigned)(H - 2));
-                float2 w00, w01, w10, w11;
-                int oa, ob, dxa, dxb, dya, dyb;
-                if (__all_sync(0xffffffffu, inb)) {
-                    // fast path: all 4 taps of every lane are inside the image
-                    const float2 x0f = add2(tx, bc2(-kMagic)), y0f = add2(ty, bc2(-kMagic));
-                    const float2 wx1 = add2(add2(ux, bc2(-0.5f)), neg2(x0f)), wy1 = add2(add2(uy, bc2(-0.5f)), neg2(y0f));
-                    const float2 wx0 = add2(bc2(1.0f), neg2(wx1)), wy0 = add2(bc2(1.0f), neg2(wy1));
-                    w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
-                    oa = y0a * W + x0a; ob = y0b * W + x0b;
-                    dxa = dxb = 1; dya = dyb = W;
-                } else {
-                    // border path: per-tap zero padding exactly like F.grid_sample(padding_mode="zeros"): clamp the tap
-                    // address, zero the weight of every tap that falls outside the image
-                    float wx0s[2], wx1s[2], wy0s[2], wy1s[2];
-                    int os[2], dxs[2], dys[2];
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        float sxk = (k ? ux.y : ux.x) - 0.5f, syk = (k ? uy.y : uy.x) - 0.5f;
-                        sxk = fminf(fmaxf(sxk, sx_lo), sx_hi);
-                        syk = fminf(fmaxf(syk, sy_lo), sy_hi);
-                        const float x0f = floorf(sxk), y0f = floorf(syk);
-                        float wx1 = sxk - x0f, wy1 = syk - y0f;
-                        float wx0 = (x0f + 1.0f) - sxk, wy0 = (y0f + 1.0f) - syk;
-                        const int x0 = (int)x0f, y0 = (int)y0f;
-                        if ((unsigned)x0 >= (unsigned)W) wx0 = 0.f;
-                        if ((unsigned)(x0 + 1) >= (unsigned)W) wx1 = 0.f;
-                        if ((unsigned)y0 >= (unsigned)H) wy0 = 0.f;
-                        if ((unsigned)(y0 + 1) >= (unsigned)H) wy1 = 0.f;
-                        const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
-                        const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
-                        wx0s[k] = wx0; wx1s[k] = wx1; wy0s[k] = wy0; wy1s[k] = wy1;
-                        os[k] = ya * W + xa; dxs[k] = xb - xa; dys[k] = (yb - ya) * W;
-                    }
-                    const float2 wx0 = make_float2(wx0s[0], wx0s[1]), wx1 = make_float2(wx1s[0], wx1s[1]);
-                    const float2 wy0 = make_float2(wy0s[0], wy0s[1]), wy1 = make_float2(wy1s[0], wy1s[1]);
-                    w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
-                    oa = os[0]; ob = os[1]; dxa = dxs[0]; dxb = dxs[1]; dya = dys[0]; dyb = dys[1];
-                }
-                // the source row the next row step will newly touch: bring its lines into L1 now (no registers held)
-                const int pfa = min(oa + 2 * W, planei - 1), pfb = min(ob + 2 * W, planei - 1);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float* pa0 = img + (oa + c * planei);
-                    const float* pb0 = img + (ob + c * planei);
-                    const float* pa1 = pa0 + dya;
-                    const float* pb1 = pb0 + dyb;
-                    const float2 i00 = make_float2(__ldg(pa0), __ldg(pb0));
-                    const float2 i01 = make_float2(__ldg(pa0 + dxa), __ldg(pb0 + dxb));
-                    const float2 i10 = make_float2(__ldg(pa1), __ldg(pb1));
-                    const float2 i11 = make_float2(__ldg(pa1 + dxa), __ldg(pb1 + dxb));
-                    prefetch_l1(img + (pfa + c * planei));
-                    prefetch_l1(img + (pfb + c * planei));
-                    float2 val = fma2(i00, w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
-                    val = fma2(i01, w01, val);
-                    val = fma2(i10, w10, val);
-                    val = fma2(i11, w11, val);
-                    xbuf[c * kRowStride + lane + 1] = val.x;
-                    xbuf[c * kRowStride + lane + 33] = val.y;
-                }
-            }
+        auto step = [&](auto tag, const int t) {
+            warp_row(c1, rlo - 2 + t, xbuf);
             __syncwarp();
-            // ---------- stage 2: lane owns buffer columns 2l, 2l+1 (a pair) ----------
-            const float* yrow = ys_l + (r + 2) * kRowStride;
-            float2 nn[3], dd[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float2 xl = *reinterpret_cast<const float2*>(xs_l + c * kRowStride);      // cols 2l-1, 2l
-                const float2 xr = *reinterpret_cast<const float2*>(xs_l + c * kRowStride + 2);  // cols 2l+1, 2l+2
-                const float2 yl = *reinterpret_cast<const float2*>(yrow + c * ych);
-                const float2 yr = *reinterpret_cast<const float2*>(yrow + c * ych + 2);
-                const float2 xxl = mul2(xl, xl), xxr = mul2(xr, xr), xyl = mul2(xl, yl), xyr = mul2(xr, yr);
-                const float m1 = xl.y + xr.x, mx = xxl.y + xxr.x, my = xyl.y + xyr.x;
-                const float2 h1 = make_float2(xl.x + m1, m1 + xr.y);
-                const float2 hx = make_float2(xxl.x + mx, mx + xxr.y);
-                const float2 hy = make_float2(xyl.x + my, my + xyr.y);
-                if (t >= 2) {
-                    const float4 k4 = cs_l[c * cch + r * (kTileCols / 2)];
-                    ssim_nd(add2(add2(hs1[P1][c], hs1[P2][c]), h1), add2(add2(hsx[P1][c], hsx[P2][c]), hx),
-                            add2(add2(hsy[P1][c], hsy[P2][c]), hy), make_float2(k4.x, k4.y), make_float2(k4.z, k4.w),
-                            nn[c], dd[c]);
-                }
-                hs1[P][c] = h1; hsx[P][c] = hx; hsy[P][c] = hy;
-            }
-            if (t >= 2) {
-                const float2 q0 = mul2(nn[0], make_float2(fast_rcp(dd[0].x), fast_rcp(dd[0].y)));
-                const float2 q1 = mul2(nn[1], make_float2(fast_rcp(dd[1].x), fast_rcp(dd[1].y)));
-                const float2 q2 = mul2(nn[2], make_float2(fast_rcp(dd[2].x), fast_rcp(dd[2].y)));
-                // clamp((1 - q) / 2, 0, 1)   (layers.py:137)
-                const float2 e0 = make_float2(__saturatef(fmaf(-0.5f, q0.x, 0.5f)), __saturatef(fmaf(-0.5f, q0.y, 0.5f)));
-                const float2 e1 = make_float2(__saturatef(fmaf(-0.5f, q1.x, 0.5f)), __saturatef(fmaf(-0.5f, q1.y, 0.5f)));
-                const float2 e2 = make_float2(__saturatef(fmaf(-0.5f, q2.x, 0.5f)), __saturatef(fmaf(-0.5f, q2.y, 0.5f)));
-                const float2 E = fma2(cw2, e2, fma2(cw1, e1, mul2(cw0, e0)));
-                const float eL = __shfl_up_sync(0xffffffffu, E.y, 1);
-                const float eR = __shfl_down_sync(0xffffffffu, E.x, 1);
-                const float mid = E.x + E.y;
-                const float2 hEc = make_float2(eL + mid, mid + eR);
-                if (t >= 4) {
-                    // single-frame volume 1 - 2 sad (monorec_model.py:251) straight to HBM; the validity mask is applied by
-                    // the per-pixel phase below (which zeroes invalid pixels) once all planes are known
-                    const float2 sad = add2(add2(hE[P1], hE[P2]), hEc);
-                    const float2 sv = fma2(bc2(-2.0f), sad, bc2(1.0f));
-                    float* o = out_d + (size_t)(r - 2) * W;
-                    if (v0 + r - 2 < H) {
-                        if (st_pair) {
-                            st_hint_f2(o, sv, pol_keep);
-                        } else {
-                            if (st0) st_hint_f1(o, sv.x, pol_keep);
-                            if (st1) st_hint_f1(o + 1, sv.y, pol_keep);
-                        }
-                    }
-                }
-                hE[P] = hEc;
-            }
+            ssim_row<decltype(tag)::value>(st, c2, t, rlo - 2 + t, xbuf + 2 * lane);
             __syncwarp();
         };
-
         int t = 0;
         for (; t + 2 < nsteps; t += 3) {
-            row_step(std::integral_constant<int, 0>{}, t);
-            row_step(std::integral_constant<int, 1>{}, t + 1);
-            row_step(std::integral_constant<int, 2>{}, t + 2);
+            step(std::integral_constant<int, 0>{}, t);
+            step(std::integral_constant<int, 1>{}, t + 1);
+            step(std::integral_constant<int, 2>{}, t + 2);
         }
-        if (t < nsteps) row_step(std::integral_constant<int, 0>{}, t);
-        if (t + 1 < nsteps) row_step(std::integral_constant<int, 1>{}, t + 1);
+        if (t < nsteps) step(std::integral_constant<int, 0>{}, t);
+        if (t + 1 < nsteps) step(std::integral_constant<int, 1>{}, t + 1);
     }
     __syncthreads();  // the marching warps' global stores are visible to the whole CTA from here on
 
