@@ -1,0 +1,12 @@
+#!/bin/bash
+# final verification of the round: full GPU suite, smoke, default bench, reference arm, evidence captures
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; tail -2 gpurun_out/pytest.log | cut -c1-200
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $? lines $(wc -l < gpurun_out/bench.json)"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-160 gpurun_out/bench_ref.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 6 -c 40 --csv --log-file gpurun_out/bench_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-full-model > gpurun_out/ncu_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cost_volume -s 2 -c 1 -o gpurun_out/prof_k1_final python tools/profile_cv.py > gpurun_out/ncu_k1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 2 -c 1 -o gpurun_out/prof_k2_final python tools/profile_conv.py > gpurun_out/ncu_k2.log 2>&1
+MONOREC_B200_CONV=tf32 timeout 600 python tools/profile_model.py 8 4 3 2>&1 | tail -1
+cat gpurun_out/bench.json | cut -c1-200
