@@ -144,7 +144,29 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Library chatter (NCCL's version banner, download messages, ...) must not end up next to the JSON line: everything
+    written to fd 1 during the run goes to stderr; emit() writes the one result line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -315,7 +337,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "keyframes/s", "cores": cores, "kind": "port",
                                 "sample": "1 keyframe (B=1, F=4, D=32, 256x512), best of 2 after 1 warm-up"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
