@@ -141,7 +141,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{steps} x 1 keyframe, torch CPU ops, all host threads"},
             "e2e": {"value": val, "unit": "keyframes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 _REAL_STDOUT = None
