@@ -263,3 +263,31 @@ def test_tc_halo_variant_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "tc_conv_matches_torch or tc_concat"],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_full_size_model_modes_and_graph_replay():
+    """BASELINE config 3 shape (256x512, D=32, F=4): tensor-core vs CUDA-core arithmetic agree within the TF32 tolerance,
+    and the CUDA-graph replay reproduces the eager forward bit for bit."""
+    from monorec_b200 import conv as C
+    from monorec_b200.model import GraphedMonoRec
+    from monorec_b200.synthetic import make_inputs, to_device
+    model, _ = _model_and_sd(0.7)
+    data = to_device(make_inputs(2, 4, 256, 512, seed=23), DEV)
+    old = C.MODE
+    try:
+        C.set_mode("fp32")
+        ref = model(dict(data))
+        ref_res, ref_mask = ref["result"].clone(), ref["cv_mask"].clone()
+        C.set_mode("tf32")
+        out = model(dict(data))
+        res, mask = out["result"].clone(), out["cv_mask"].clone()
+        g = GraphedMonoRec(model, data)
+        rep = g(data)
+        torch.cuda.synchronize()
+        assert torch.equal(rep["result"], res) and torch.equal(rep["cv_mask"], mask)
+    finally:
+        C.set_mode(old)
+    dr, dm = (res - ref_res).abs().max().item(), (mask - ref_mask).abs().max().item()
+    print("full size tf32 vs fp32: inverse depth max|d|", dr, "mask max|d|", dm)
+    assert dr < 1e-3 and dm < 5e-3
+    assert res.shape == (2, 1, 256, 512) and [p.shape[-1] for p in out["predicted_inverse_depths"]] == [512, 256, 128, 64]
