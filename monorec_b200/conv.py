@@ -135,6 +135,8 @@ def conv_transpose_k4s2_crop(srcs, sub_weights, bias, act=ACT_LEAKY, act_a=LEAKY
 def nchw_to_nhwc(x, out=None, out_coff=0, one_minus=None):
     """(B,C,H,W) -> NHWC (optionally into a channel slice of `out`, optionally scaled by (1 - one_minus[b,0,h,w]))."""
     lib = _lib.load()
+    if out is None and one_minus is None and x.dim() == 4 and x.dtype == torch.float32 and x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1)          # already channels-last in memory (e.g. cuDNN NHWC output): a view, no kernel
     x = x.contiguous()
     B, C, H, W = x.shape
     if out is None:

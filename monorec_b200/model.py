@@ -337,6 +337,7 @@ class MonoRecModel(nn.Module):
             for param in module.parameters(True):
                 param.requires_grad_(False)
         self.augmenter = None
+        self._trunk_channels_last = False
 
     # -- checkpoint loading: same key filtering as utils/util.py:244-248 + monorec_model.py:630-657 ------------------
     @staticmethod
@@ -385,7 +386,14 @@ class MonoRecModel(nn.Module):
                 data_dict["cost_volume"] = keyframe.new_zeros(s)
                 data_dict["single_frame_cvs"] = [data_dict["cost_volume"].clone() for _ in data_dict["poses"]]
 
-            data_dict["image_features"] = self._feature_extractor(keyframe + .5)
+            # torchvision trunk on cuDNN: channels-last so that its outputs are already NHWC for the conv engine (the dict
+            # still holds logical (B,C,H,W) tensors); TF32 is allowed there exactly when the engine itself runs TF32
+            if not self._trunk_channels_last:
+                self._feature_extractor.to(memory_format=torch.channels_last)
+                self._trunk_channels_last = True
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=(C.MODE == "tf32")):
+                data_dict["image_features"] = self._feature_extractor(
+                    (keyframe + .5).contiguous(memory_format=torch.channels_last))
 
             if self.pretrain_mode == 0 or self.pretrain_mode == 2:
                 data_dict = self.att_module(data_dict)
