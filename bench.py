@@ -15,7 +15,6 @@ primitives in the same order, pinned on golden vectors from the reference) on th
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time

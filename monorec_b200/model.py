@@ -8,10 +8,9 @@ convolution engine) through the C ABI.  The ResNet-18 trunk stays on torchvision
 reference too; SURVEY.md §8f "next" row 1).
 """
 import torch
-import torch.nn.functional as F
 from torch import nn
 
-from . import _lib, conv as C
+from . import conv as C
 from .cost_volume import CostVolumeModule
 
 __all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "ResnetEncoder"]

@@ -1,5 +1,4 @@
 """Times representative conv layers of the stacks on the tensor-core path (CUDA events), halo variant on/off via env."""
-import os
 import sys
 from pathlib import Path
 

@@ -1,6 +1,5 @@
 """Times the full MonoRecModel forward and its stages on cuda:0 (CUDA events), synthetic KITTI-shaped inputs."""
 import sys
-import time
 from pathlib import Path
 
 import torch
