@@ -194,7 +194,10 @@ __device__ __forceinline__ void warp_row(const Stage1Ctx& c, const int r, float*
         oa = os[0]; ob = os[1]; dxa = dxs[0]; dxb = dxs[1]; dya = dys[0]; dyb = dys[1];
     }
     // the source row the next row step will newly touch: bring its lines into L1 now (no registers held)
-    const int pfa = min(oa + 2 * W, c.planei - 1), pfb = min(ob + 2 * W, c.planei - 1);
+#ifndef MR_CV_PF_ROWS
+#define MR_CV_PF_ROWS 0     // rows ahead for an explicit L1 prefetch of the next source row; measured: 0 (off) is 11 % faster
+#endif
+    const int pfa = min(oa + MR_CV_PF_ROWS * W, c.planei - 1), pfb = min(ob + MR_CV_PF_ROWS * W, c.planei - 1);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float* pa0 = c.img + (oa + ch * c.planei);
@@ -205,8 +208,10 @@ __device__ __forceinline__ void warp_row(const Stage1Ctx& c, const int r, float*
         const float2 i01 = make_float2(__ldg(pa0 + dxa), __ldg(pb0 + dxb));
         const float2 i10 = make_float2(__ldg(pa1), __ldg(pb1));
         const float2 i11 = make_float2(__ldg(pa1 + dxa), __ldg(pb1 + dxb));
-        prefetch_l1(c.img + (pfa + ch * c.planei));
-        prefetch_l1(c.img + (pfb + ch * c.planei));
+        if (MR_CV_PF_ROWS > 0) {
+            prefetch_l1(c.img + (pfa + ch * c.planei));
+            prefetch_l1(c.img + (pfb + ch * c.planei));
+        }
         float2 val = fma2(i00, w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
         val = fma2(i01, w01, val);
         val = fma2(i10, w10, val);
@@ -242,12 +247,15 @@ struct Stage2State {
     }
 };
 
-template <int P>
-__device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, const int t, const int r,
-                                         const float* __restrict__ xs_l) {
+// STAGE selects how far the two cascaded 3x3 windows are filled: 0 = rows 0,1 of a unit (only the horizontal sums are
+// recorded), 1 = rows 2,3 (SSIM error row available, patch window not yet), 2 = steady state (a cost row is stored).
+// Making it a template parameter keeps the steady-state step one branch-free block, so the three channels' dependency
+// chains are scheduled against each other.
+template <int P, int STAGE>
+__device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, const int r, const float* __restrict__ xs_l) {
     constexpr int P1 = (P + 1) % 3, P2 = (P + 2) % 3;
     const float* yrow = c.ys_l + (r + 2) * kRowStride;
-    float2 nn[3], dd[3];
+    float2 h1[3], hx[3], hy[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const float2 xl = *reinterpret_cast<const float2*>(xs_l + ch * kRowStride);      // cols 2l-1, 2l
@@ -256,18 +264,19 @@ __device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, co
         const float2 yr = *reinterpret_cast<const float2*>(yrow + ch * c.ych + 2);
         const float2 xxl = mul2(xl, xl), xxr = mul2(xr, xr), xyl = mul2(xl, yl), xyr = mul2(xr, yr);
         const float m1 = xl.y + xr.x, mx = xxl.y + xxr.x, my = xyl.y + xyr.x;
-        const float2 h1 = make_float2(xl.x + m1, m1 + xr.y);
-        const float2 hx = make_float2(xxl.x + mx, mx + xxr.y);
-        const float2 hy = make_float2(xyl.x + my, my + xyr.y);
-        if (t >= 2) {
+        h1[ch] = make_float2(xl.x + m1, m1 + xr.y);
+        hx[ch] = make_float2(xxl.x + mx, mx + xxr.y);
+        hy[ch] = make_float2(xyl.x + my, my + xyr.y);
+    }
+    if (STAGE >= 1) {
+        float2 nn[3], dd[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
             const float4 k4 = c.cs_l[ch * c.cch + r * (kTileCols / 2)];
-            ssim_nd(add2(add2(st.hs1[P1][ch], st.hs1[P2][ch]), h1), add2(add2(st.hsx[P1][ch], st.hsx[P2][ch]), hx),
-                    add2(add2(st.hsy[P1][ch], st.hsy[P2][ch]), hy), make_float2(k4.x, k4.y), make_float2(k4.z, k4.w),
+            ssim_nd(add2(add2(st.hs1[P1][ch], st.hs1[P2][ch]), h1[ch]), add2(add2(st.hsx[P1][ch], st.hsx[P2][ch]), hx[ch]),
+                    add2(add2(st.hsy[P1][ch], st.hsy[P2][ch]), hy[ch]), make_float2(k4.x, k4.y), make_float2(k4.z, k4.w),
                     nn[ch], dd[ch]);
         }
-        st.hs1[P][ch] = h1; st.hsx[P][ch] = hx; st.hsy[P][ch] = hy;
-    }
-    if (t >= 2) {
         const float2 q0 = mul2(nn[0], make_float2(fast_rcp(dd[0].x), fast_rcp(dd[0].y)));
         const float2 q1 = mul2(nn[1], make_float2(fast_rcp(dd[1].x), fast_rcp(dd[1].y)));
         const float2 q2 = mul2(nn[2], make_float2(fast_rcp(dd[2].x), fast_rcp(dd[2].y)));
@@ -280,7 +289,7 @@ __device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, co
         const float eR = __shfl_down_sync(0xffffffffu, E.x, 1);
         const float mid = E.x + E.y;
         const float2 hEc = make_float2(eL + mid, mid + eR);
-        if (t >= 4) {
+        if (STAGE >= 2) {
             // single-frame volume 1 - 2 sad (monorec_model.py:251) straight to HBM; the validity mask is applied by the
             // per-pixel phase (which zeroes invalid pixels) once all planes are known
             const float2 sad = add2(add2(st.hE[P1], st.hE[P2]), hEc);
@@ -297,8 +306,9 @@ __device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, co
         }
         st.hE[P] = hEc;
     }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) { st.hs1[P][ch] = h1[ch]; st.hsx[P][ch] = hx[ch]; st.hsy[P][ch] = hy[ch]; }
 }
-
 
 __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(const CvArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -406,7 +416,10 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
     Stage1Ctx c1;
     c1.W = W; c1.H = H; c1.planei = planei; c1.v0 = v0; c1.lane = lane;
     c1.sx_lo = sx_lo; c1.sx_hi = sx_hi; c1.sy_lo = sy_lo; c1.sy_hi = sy_hi;
-    for (int unit = warp; unit < F * D; unit += kWarps) {
+#ifndef MR_CV_SKIP
+#define MR_CV_SKIP 0     // timing experiments only: 1 = no march, 2 = no per-pixel phase, 3 = march without stage 2, 4 = march without stage 1
+#endif
+    for (int unit = warp; unit < F * D && MR_CV_SKIP != 1; unit += kWarps) {
         const int f = unit / D, d = unit - f * D;
         const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
         if (rhi < rlo) continue;  // no valid pixel of this tile for frame f: the per-pixel phase zero-fills
@@ -415,20 +428,28 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
         st.clear();
         c2.out_d = a.sfcv + (((size_t)f * a.B + b) * D + d) * plane + (size_t)v0 * W + ucol;
         const int nsteps = rhi - rlo + 5;
-        auto step = [&](auto tag, const int t) {
-            warp_row(c1, rlo - 2 + t, xbuf);
+        auto step = [&](auto tag, auto stage, const int t) {
+            if (MR_CV_SKIP != 4) warp_row(c1, rlo - 2 + t, xbuf);
             __syncwarp();
-            ssim_row<decltype(tag)::value>(st, c2, t, rlo - 2 + t, xbuf + 2 * lane);
+            if (MR_CV_SKIP != 3) ssim_row<decltype(tag)::value, decltype(stage)::value>(st, c2, rlo - 2 + t, xbuf + 2 * lane);
             __syncwarp();
         };
-        int t = 0;
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+        // window fill (nsteps >= 5 always), then the branch-free steady state
+        step(I0{}, I0{}, 0);
+        step(I1{}, I0{}, 1);
+        step(I2{}, I1{}, 2);
+        step(I0{}, I1{}, 3);
+        int t = 4;
         for (; t + 2 < nsteps; t += 3) {
-            step(std::integral_constant<int, 0>{}, t);
-            step(std::integral_constant<int, 1>{}, t + 1);
-            step(std::integral_constant<int, 2>{}, t + 2);
+            step(I1{}, I2{}, t);
+            step(I2{}, I2{}, t + 1);
+            step(I0{}, I2{}, t + 2);
         }
-        if (t < nsteps) step(std::integral_constant<int, 0>{}, t);
-        if (t + 1 < nsteps) step(std::integral_constant<int, 1>{}, t + 1);
+        if (t < nsteps) step(I1{}, I2{}, t);
+        if (t + 1 < nsteps) step(I2{}, I2{}, t + 1);
     }
     __syncthreads();  // the marching warps' global stores are visible to the whole CTA from here on
 
@@ -436,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
     //      cv = sum_f w_f (1 - 2 sad_f) / sum_f w_f, 0 where sum_f w_f == 0 (:262-269).  Each thread reads back the
     //      L2-hot single-frame values of its pixel once per frame. ------------------------------------------------------
     const float na4 = -0.25f * a.alpha;
-    for (int p = tid; p < TH * kTileCols; p += kThreads) {
+    for (int p = tid; p < TH * kTileCols && MR_CV_SKIP != 2; p += kThreads) {
         const int r = p >> 6, bc = p & 63;
         const int u = u0 + bc, v = v0 + r;
         const bool own = (bc >= 2) && (bc < 2 + kOutCols) && (u < W) && (v < H);
