@@ -74,6 +74,15 @@ int mr_cost_volume_fwd(const float* keyframe, const float* const* frames, const 
                        float alpha, const float* chan_w /* host, 3 floats, NULL = reference default */,
                        void* stream);
 
+/* The same kernel with a caller-owned device workspace of mr_cost_volume_workspace_bytes(B,F,H,W) bytes (16-byte aligned):
+ * the source frames are first re-laid as (r,g,b,0) pixels so that every bilinear tap is one 16-byte load (the gather stage
+ * is bound by L1/LSU requests); results are bit-identical to mr_cost_volume_fwd. */
+long long mr_cost_volume_workspace_bytes(int B, int F, int H, int W);
+int mr_cost_volume_fwd_ws(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
+                          float* out_cv, float* out_sfcv,
+                          int B, int F, int D, int H, int W,
+                          float alpha, const float* chan_w, void* workspace, long long workspace_bytes, void* stream);
+
 /* Same path with HOST buffers (pinned or pageable): uploads the images and matrices, runs
  * mr_projection_tables + mr_cost_volume_fwd and downloads both volumes; batch elements are pipelined on
  * internal streams so copies overlap the kernel.  This is the end-to-end entry bench.py times as `e2e`.

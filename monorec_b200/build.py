@@ -15,7 +15,7 @@ STAMP = PKG / ".libmonorec_b200.stamp"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math_off_placeholder"]
 FLAGS = [f for f in FLAGS if not f.endswith("_placeholder")]
-for _knob in ("MR_CV_THREADS", "MR_CV_MINBLOCKS", "MR_CV_TILE_ROWS", "MR_CV_SKIP", "MR_CV_PF_ROWS"):   # tuning knobs of the cost-volume kernel
+for _knob in ("MR_CV_THREADS", "MR_CV_MINBLOCKS", "MR_CV_TILE_ROWS", "MR_CV_SKIP"):   # tuning knobs of the cost-volume kernel
     if os.environ.get(_knob):
         FLAGS.append(f"-D{_knob}=" + os.environ[_knob])
 

@@ -47,6 +47,7 @@ struct CvArgs {
     const float* depths;                 // [D]
     float* cv;                           // [B,D,H,W]
     float* sfcv;                         // [F,B,D,H,W]
+    const float4* packed;                // [F,B,H,W] (r,g,b,0) copies of the source frames, or nullptr (planar gather)
     int B, F, D, H, W, TH, b0;
     float alpha, inv_dm1;
     float cw0, cw1, cw2;                 // channel weights / 9
@@ -103,7 +104,6 @@ __device__ __forceinline__ void st_hint_f1(float* ptr, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(pol) : "memory");
 }
 
-__device__ __forceinline__ void prefetch_l1(const float* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 constexpr int kChunk = 32;                 // planes the per-pixel phase keeps in registers at once
 constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
@@ -126,6 +126,7 @@ struct Stage1Ctx {
     float2 pzx, pzy, pzz;             // per-lane column part of the projection (already times the plane depth)
     float rax, rbx, ray, rby, raz, rbz;  // per-row part: c = pz(u) + ra * v + rb
     const float* img;                 // source frame of this batch element, [3][H][W]
+    const float4* img4;               // the same frame as [H][W] (r,g,b,0) pixels (packed gather) or nullptr
     int W, H, planei, v0, lane;
     float sx_lo, sx_hi, sy_lo, sy_hi; // == grid clamp(-2, 2), monorec_model.py:208
 };
@@ -141,6 +142,7 @@ __device__ __forceinline__ void setup_stage1(Stage1Ctx& c, const float* m, const
     c.img = img;
 }
 
+template <bool PACKED>
 __device__ __forceinline__ void warp_row(const Stage1Ctx& c, const int r, float* __restrict__ xrow) {
     const int W = c.W, H = c.H;
     const float fv = (float)(c.v0 + r);
@@ -193,31 +195,39 @@ __device__ __forceinline__ void warp_row(const Stage1Ctx& c, const int r, float*
         w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
         oa = os[0]; ob = os[1]; dxa = dxs[0]; dxb = dxs[1]; dya = dys[0]; dyb = dys[1];
     }
-    // the source row the next row step will newly touch: bring its lines into L1 now (no registers held)
-#ifndef MR_CV_PF_ROWS
-#define MR_CV_PF_ROWS 0     // rows ahead for an explicit L1 prefetch of the next source row; measured: 0 (off) is 11 % faster
-#endif
-    const int pfa = min(oa + MR_CV_PF_ROWS * W, c.planei - 1), pfb = min(ob + MR_CV_PF_ROWS * W, c.planei - 1);
+    if (PACKED) {
+        // one 16-byte load per tap: 8 requests per row step instead of 24 (stage 1 is bound by L1/LSU requests)
+        const float4* qa = c.img4 + oa;
+        const float4* qb = c.img4 + ob;
+        const float4 a00 = __ldg(qa), a01 = __ldg(qa + dxa), a10 = __ldg(qa + dya), a11 = __ldg(qa + dya + dxa);
+        const float4 b00 = __ldg(qb), b01 = __ldg(qb + dxb), b10 = __ldg(qb + dyb), b11 = __ldg(qb + dyb + dxb);
+        float2 v0 = fma2(make_float2(a00.x, b00.x), w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
+        float2 v1 = fma2(make_float2(a00.y, b00.y), w00, bc2(0.5f));
+        float2 v2 = fma2(make_float2(a00.z, b00.z), w00, bc2(0.5f));
+        v0 = fma2(make_float2(a01.x, b01.x), w01, v0); v1 = fma2(make_float2(a01.y, b01.y), w01, v1); v2 = fma2(make_float2(a01.z, b01.z), w01, v2);
+        v0 = fma2(make_float2(a10.x, b10.x), w10, v0); v1 = fma2(make_float2(a10.y, b10.y), w10, v1); v2 = fma2(make_float2(a10.z, b10.z), w10, v2);
+        v0 = fma2(make_float2(a11.x, b11.x), w11, v0); v1 = fma2(make_float2(a11.y, b11.y), w11, v1); v2 = fma2(make_float2(a11.z, b11.z), w11, v2);
+        xrow[c.lane + 1] = v0.x;                  xrow[c.lane + 33] = v0.y;
+        xrow[kRowStride + c.lane + 1] = v1.x;     xrow[kRowStride + c.lane + 33] = v1.y;
+        xrow[2 * kRowStride + c.lane + 1] = v2.x; xrow[2 * kRowStride + c.lane + 33] = v2.y;
+    } else {
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float* pa0 = c.img + (oa + ch * c.planei);
-        const float* pb0 = c.img + (ob + ch * c.planei);
-        const float* pa1 = pa0 + dya;
-        const float* pb1 = pb0 + dyb;
-        const float2 i00 = make_float2(__ldg(pa0), __ldg(pb0));
-        const float2 i01 = make_float2(__ldg(pa0 + dxa), __ldg(pb0 + dxb));
-        const float2 i10 = make_float2(__ldg(pa1), __ldg(pb1));
-        const float2 i11 = make_float2(__ldg(pa1 + dxa), __ldg(pb1 + dxb));
-        if (MR_CV_PF_ROWS > 0) {
-            prefetch_l1(c.img + (pfa + ch * c.planei));
-            prefetch_l1(c.img + (pfb + ch * c.planei));
+        for (int ch = 0; ch < 3; ++ch) {
+            const float* pa0 = c.img + (oa + ch * c.planei);
+            const float* pb0 = c.img + (ob + ch * c.planei);
+            const float* pa1 = pa0 + dya;
+            const float* pb1 = pb0 + dyb;
+            const float2 i00 = make_float2(__ldg(pa0), __ldg(pb0));
+            const float2 i01 = make_float2(__ldg(pa0 + dxa), __ldg(pb0 + dxb));
+            const float2 i10 = make_float2(__ldg(pa1), __ldg(pb1));
+            const float2 i11 = make_float2(__ldg(pa1 + dxa), __ldg(pb1 + dxb));
+            float2 val = fma2(i00, w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
+            val = fma2(i01, w01, val);
+            val = fma2(i10, w10, val);
+            val = fma2(i11, w11, val);
+            xrow[ch * kRowStride + c.lane + 1] = val.x;
+            xrow[ch * kRowStride + c.lane + 33] = val.y;
         }
-        float2 val = fma2(i00, w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
-        val = fma2(i01, w01, val);
-        val = fma2(i10, w10, val);
-        val = fma2(i11, w11, val);
-        xrow[ch * kRowStride + c.lane + 1] = val.x;
-        xrow[ch * kRowStride + c.lane + 33] = val.y;
     }
 }
 
@@ -310,6 +320,7 @@ __device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, co
     for (int ch = 0; ch < 3; ++ch) { st.hs1[P][ch] = h1[ch]; st.hsx[P][ch] = hx[ch]; st.hsy[P][ch] = hy[ch]; }
 }
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(const CvArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = make_layout(a.D, a.TH, a.F);
@@ -424,12 +435,13 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
         const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
         if (rhi < rlo) continue;  // no valid pixel of this tile for frame f: the per-pixel phase zero-fills
         setup_stage1(c1, pjs + 12 * f, a.frames[f] + (size_t)b * 3 * plane, zs[d], fu2);
+        c1.img4 = PACKED ? a.packed + ((size_t)f * a.B + b) * plane : nullptr;
         Stage2State st;
         st.clear();
         c2.out_d = a.sfcv + (((size_t)f * a.B + b) * D + d) * plane + (size_t)v0 * W + ucol;
         const int nsteps = rhi - rlo + 5;
         auto step = [&](auto tag, auto stage, const int t) {
-            if (MR_CV_SKIP != 4) warp_row(c1, rlo - 2 + t, xbuf);
+            if (MR_CV_SKIP != 4) warp_row<PACKED>(c1, rlo - 2 + t, xbuf);
             __syncwarp();
             if (MR_CV_SKIP != 3) ssim_row<decltype(tag)::value, decltype(stage)::value>(st, c2, rlo - 2 + t, xbuf + 2 * lane);
             __syncwarp();
@@ -590,6 +602,15 @@ __global__ void projection_tables_kernel(const float* kf_pose, const float* kf_K
     }
 }
 
+// Source frames re-laid as (r,g,b,0) pixels so that a bilinear tap is one 16-byte load (see warp_row<true>).
+__global__ void repack_frames_kernel(PtrPack frames, float4* __restrict__ packed, int B, int HW, int b0) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int b = b0 + blockIdx.y, f = blockIdx.z;
+    const float* src = frames.p[f] + (size_t)b * 3 * HW + p;
+    packed[((size_t)f * B + b) * HW + p] = make_float4(__ldg(src), __ldg(src + HW), __ldg(src + 2 * (size_t)HW), 0.f);
+}
+
 #ifndef MR_CV_TILE_ROWS
 #define MR_CV_TILE_ROWS 16
 #endif
@@ -625,7 +646,8 @@ extern "C" int mr_projection_tables(const float* keyframe_pose, const float* key
 
 int mr::launch_cost_volume(const float* keyframe, const float* const* frames, const float* proj,
                            const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H, int W,
-                           float alpha, const float* chan_w, int b_begin, int b_count, cudaStream_t stream) {
+                           float alpha, const float* chan_w, int b_begin, int b_count, void* workspace,
+                           long long workspace_bytes, cudaStream_t stream) {
     MR_REQUIRE(keyframe && frames && proj && depths && out_cv && out_sfcv, "mr_cost_volume_fwd: null pointer");
     MR_REQUIRE(b_begin >= 0 && b_count >= 1 && b_begin + b_count <= B, "mr_cost_volume_fwd: bad batch range");
     MR_REQUIRE(B >= 1 && B <= 65535, "mr_cost_volume_fwd: batch %d out of range", B);
@@ -648,16 +670,45 @@ int mr::launch_cost_volume(const float* keyframe, const float* const* frames, co
     const float* cw = chan_w ? chan_w : def_w;
     a.cw0 = cw[0] / 9.f; a.cw1 = cw[1] / 9.f; a.cw2 = cw[2] / 9.f;  // monorec_model.py:141 (weights / patch_size^2)
     const SmemLayout L = make_layout(D, a.TH, F);
-    MR_CUDA(cudaFuncSetAttribute(cost_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     dim3 grid((W + kOutCols - 1) / kOutCols, (H + a.TH - 1) / a.TH, b_count);
-    cost_volume_kernel<<<grid, kThreads, L.total, stream>>>(a);
+    if (workspace != nullptr) {
+        MR_REQUIRE(workspace_bytes >= mr_cost_volume_workspace_bytes(B, F, H, W),
+                   "mr_cost_volume_fwd_ws: workspace too small (%lld < %lld bytes)", workspace_bytes,
+                   mr_cost_volume_workspace_bytes(B, F, H, W));
+        MR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "mr_cost_volume_fwd_ws: workspace must be 16-byte aligned");
+        a.packed = static_cast<const float4*>(workspace);
+        PtrPack fp{};
+        for (int f = 0; f < F; ++f) fp.p[f] = frames[f];
+        dim3 rgrid((H * W + 255) / 256, b_count, F);
+        repack_frames_kernel<<<rgrid, 256, 0, stream>>>(fp, static_cast<float4*>(workspace), B, H * W, b_begin);
+        MR_LAUNCH_CHECK("repack_frames_kernel");
+        MR_CUDA(cudaFuncSetAttribute(cost_volume_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        cost_volume_kernel<true><<<grid, kThreads, L.total, stream>>>(a);
+    } else {
+        MR_CUDA(cudaFuncSetAttribute(cost_volume_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        cost_volume_kernel<false><<<grid, kThreads, L.total, stream>>>(a);
+    }
     MR_LAUNCH_CHECK("cost_volume_kernel");
     return MR_OK;
+}
+
+extern "C" long long mr_cost_volume_workspace_bytes(int B, int F, int H, int W) {
+    if (B < 1 || F < 1 || H < 1 || W < 1) return 0;
+    return (long long)F * B * H * W * 16;
+}
+
+extern "C" int mr_cost_volume_fwd_ws(const float* keyframe, const float* const* frames, const float* proj,
+                                     const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H, int W,
+                                     float alpha, const float* chan_w, void* workspace, long long workspace_bytes,
+                                     void* stream) {
+    MR_REQUIRE(workspace != nullptr, "mr_cost_volume_fwd_ws: null workspace");
+    return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0, B,
+                                  workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int mr_cost_volume_fwd(const float* keyframe, const float* const* frames, const float* proj,
                                   const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H,
                                   int W, float alpha, const float* chan_w, void* stream) {
     return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0,
-                                  B, (cudaStream_t)stream);
+                                  B, nullptr, 0, (cudaStream_t)stream);
 }

@@ -189,3 +189,21 @@ def test_hires_config_small_batch():
     cvp, sfp = _run(pd, steps=64)
     assert all(torch.equal(sfp[j], sf[perm[j]]) for j in range(6))
     assert (cvp - cv).abs().max() <= 1e-5
+
+
+def test_packed_and_planar_gather_are_bit_identical():
+    """mr_cost_volume_fwd_ws ((r,g,b,0)-packed source copies, one 16-byte load per tap) == mr_cost_volume_fwd (planar)."""
+    from monorec_b200.cost_volume import CostVolumeModule
+    from monorec_b200.synthetic import make_inputs, to_device
+    data = make_inputs(2, 3, 96, 200, seed=55)
+    outs = []
+    for packed in (True, False):
+        d = to_device(data, "cuda:0")
+        d["_cv_range"] = (0.0025, 0.33, 32)
+        m = CostVolumeModule()
+        m.packed_gather = packed
+        o = m(d)
+        torch.cuda.synchronize()
+        outs.append((o["cost_volume"].cpu(), [s.cpu() for s in o["single_frame_cvs"]]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
