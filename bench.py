@@ -312,27 +312,32 @@ def main():
         from monorec_b200.model import GraphedMonoRec, MonoRecModel
         torch.manual_seed(0)
         model = MonoRecModel().to(dev).eval()          # random-init weights of the reference architecture
-        gm = GraphedMonoRec(model, sets[0])
-        fm_steps = 20
-        for i in range(3):
-            all_gather_batch(gm(sets[i % NSETS])["result"])
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for i in range(fm_steps):
-            res = all_gather_batch(gm(sets[i % NSETS])["result"])
-        f1.record()
-        barrier()
-        t = torch.tensor([f0.elapsed_time(f1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            fms = float(t.item()) / fm_steps
-            line["full_model"] = {"value": world * B / (fms * 1e-3), "unit": "keyframes/s", "ms_per_forward": fms,
-                                  "batch_per_gpu": B, "conv_arithmetic": C.MODE, "gathered_result_shape": list(res.shape),
-                                  "what": "MonoRecModel.forward (CUDA-graph replay) + NCCL all-gather of result; "
-                                          "inputs resident, random-init weights"}
-        del gm, model
+        default_mode = C.MODE
+        for key, mode in (("full_model", "tf32"), ("full_model_f16", "f16")):
+            C.set_mode(mode)
+            gm = GraphedMonoRec(model, sets[0])
+            fm_steps = 20
+            for i in range(3):
+                all_gather_batch(gm(sets[i % NSETS])["result"])
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(fm_steps):
+                res = all_gather_batch(gm(sets[i % NSETS])["result"])
+            f1.record()
+            barrier()
+            t = torch.tensor([f0.elapsed_time(f1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                fms = float(t.item()) / fm_steps
+                line[key] = {"value": world * B / (fms * 1e-3), "unit": "keyframes/s", "ms_per_forward": fms,
+                             "batch_per_gpu": B, "conv_arithmetic": mode, "gathered_result_shape": list(res.shape),
+                             "what": "MonoRecModel.forward (CUDA-graph replay) + NCCL all-gather of result; "
+                                     "inputs resident, random-init weights"}
+            del gm
+        C.set_mode(default_mode)
+        del model
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores = cpu_port_keyframes_per_s(repeats=2)

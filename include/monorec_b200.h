@@ -110,6 +110,8 @@ int mr_cost_volume_host(const float* h_keyframe, const float* h_frames,
  *   ConvTranspose2d(k4,s2)+crop (layers.py:380-400) -> four sub-pixel 2x2 convolutions written with oy_step = ox_step = 2
  */
 #define MR_CONV_MAX_SRC 3
+#define MR_DT_F32 0
+#define MR_DT_F16 1           /* IEEE half storage: tensor-core path (kind::f16, fp32 accumulate) and the helper kernels */
 #define MR_ACT_NONE 0
 #define MR_ACT_LEAKY 1     /* x >= 0 ? x : act_a * x */
 #define MR_ACT_SIGMOID 2
@@ -130,13 +132,17 @@ typedef struct mr_conv_desc {
     int oy_step, ox_step, oy_off, ox_off;    /* output (oy, ox) is stored at (oy*oy_step + oy_off, ox*ox_step + ox_off) */
     int act;
     float act_a, act_b;
+    int src_dtype, dst_dtype;                /* MR_DT_F32 / MR_DT_F16 storage of the sources (and packed tensor-core weights) /
+                                                of the destination; pointers are typed float* for historical reasons */
 } mr_conv_desc;
 
 int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
 /* Same descriptor on the tensor cores (tcgen05, kind::tf32: TF32 products, fp32 accumulation in TMEM, fp32 storage).
  * `weight` is packed as [kh*kw][n_pad][k_pad] (K contiguous): Cout padded to n_pad (multiple of 16, <= 256), every source
  * padded to a multiple of 32 channels (k_pad = sum).  Needs src_c[i] % 4 == 0 and upsample2 == 0 (nearest-x2 upsampling is
- * expressed as sub-pixel convolutions on this path).  round_out: round stored activations to TF32 (nearest). */
+ * expressed as sub-pixel convolutions on this path).  round_out: round stored activations to TF32 (nearest).
+ * With src_dtype = MR_DT_F16 the sources and the packed weights are half, a K chunk is 64 channels (k_pad counts 64s) and
+ * the MMA is kind::f16; dst_dtype selects half or float output. */
 int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream);
 /* sizeof(mr_conv_desc) as compiled into the library (bindings check their mirror of the struct against it). */
 int mr_sizeof_conv_desc(void);
@@ -145,6 +151,13 @@ int mr_sizeof_conv_desc(void);
  * scale[b,h,w] applied as (1 - scale) (monorec_model.py:713: cost_volume * (1 - cv_mask)). */
 int mr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H, int W, int dst_c, int dst_coff,
                     const float* one_minus_scale, void* stream);
+/* The same with a half destination; the layout kernels below have _f16 twins for half NHWC tensors. */
+int mr_nchw_to_nhwc_f16(const float* src, void* dst, int B, int C, int H, int W, int dst_c, int dst_coff,
+                        const float* one_minus_scale, void* stream);
+int mr_maxpool2_nhwc_f16(const void* src, void* dst, int B, int H, int W, int C, void* stream);
+int mr_max_over_frames_f16(const void* src, void* dst, int F, long long n_per_frame, void* stream);
+/* dst[i] = (half) src[i] for n contiguous fp32 values (used for channels-last feature maps). */
+int mr_cast_f32_to_f16(const float* src, void* dst, long long n, void* stream);
 /* nn.MaxPool2d(2) on NHWC (monorec_model.py:304-316). H and W must be even. */
 int mr_maxpool2_nhwc(const float* src, float* dst, int B, int H, int W, int C, void* stream);
 /* Element-wise max over the leading axis: dst[n] = max_f src[f*n_per_frame + n]  (monorec_model.py:362-365). */

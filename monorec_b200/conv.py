@@ -20,14 +20,25 @@ LEAKY_SLOPE = 0.1  # model/layers.py:290, 318, 381
 KC = 32            # channels per K chunk of the tensor-core kernel (csrc/conv_tc.cu)
 
 # Arithmetic of the dense-contraction layers: "tf32" = tcgen05 tensor cores (kind::tf32, fp32 accumulate, fp32 storage),
-# "fp32" = CUDA-core FMA kernel (bit-level parity path).  1-channel heads always use the fp32 kernel.
+# "f16" = tcgen05 kind::f16 with half NHWC activations and weights (fp32 accumulate; BASELINE config 3),
+# "fp32" = CUDA-core FMA kernel (bit-level parity path).  1-channel heads always use the CUDA-core dot-product kernel.
 MODE = os.environ.get("MONOREC_B200_CONV", "tf32").lower()
+DT_F32, DT_F16 = 0, 1
 
 
 def set_mode(mode):
     global MODE
-    assert mode in ("tf32", "fp32")
+    assert mode in ("tf32", "fp32", "f16")
     MODE = mode
+
+
+def act_dtype():
+    """torch dtype of the NHWC activations inside the engine for the current MODE."""
+    return torch.float16 if MODE == "f16" else torch.float32
+
+
+def _dt(t):
+    return DT_F16 if t.dtype == torch.float16 else DT_F32
 
 
 class ConvDesc(ctypes.Structure):
@@ -39,7 +50,7 @@ class ConvDesc(ctypes.Structure):
                 ("weight", c_void_p), ("bias", c_void_p), ("dst", c_void_p),
                 ("dst_H", c_int), ("dst_W", c_int), ("dst_c", c_int), ("dst_coff", c_int),
                 ("oy_step", c_int), ("ox_step", c_int), ("oy_off", c_int), ("ox_off", c_int),
-                ("act", c_int), ("act_a", c_float), ("act_b", c_float)]
+                ("act", c_int), ("act_a", c_float), ("act_b", c_float), ("src_dtype", c_int), ("dst_dtype", c_int)]
 
 
 def same_pad_before(n, k, s):
@@ -99,7 +110,7 @@ def conv2d(srcs, weight, bias, kh, kw, stride=(1, 1), act=ACT_NONE, act_a=0.0, a
     d.n_src = len(srcs)
     cin = 0
     for i, s in enumerate(srcs):
-        assert s.is_cuda and s.dtype == torch.float32 and s.is_contiguous(), "conv sources must be contiguous fp32 CUDA"
+        assert s.is_cuda and s.dtype == x0.dtype and s.is_contiguous(), "conv sources must be contiguous CUDA tensors of one dtype"
         assert s.shape[:3] == x0.shape[:3], "concatenated sources must share B, H, W"
         d.src[i] = s.data_ptr()
         d.src_c[i] = s.shape[3]
@@ -114,6 +125,7 @@ def conv2d(srcs, weight, bias, kh, kw, stride=(1, 1), act=ACT_NONE, act_a=0.0, a
     d.dst_H, d.dst_W, d.dst_c, d.dst_coff = out.shape[1], out.shape[2], out.shape[3], out_coff
     d.oy_step, d.ox_step, d.oy_off, d.ox_off = out_step[0], out_step[1], out_off[0], out_off[1]
     d.act, d.act_a, d.act_b = act, act_a, act_b
+    d.src_dtype, d.dst_dtype = _dt(x0), _dt(out)
     with torch.cuda.device(x0.device):
         _lib.check(lib.mr_conv2d_nhwc(ctypes.byref(d), _stream(x0)), "mr_conv2d_nhwc")
     return out
@@ -132,28 +144,37 @@ def conv_transpose_k4s2_crop(srcs, sub_weights, bias, act=ACT_LEAKY, act_a=LEAKY
     return out
 
 
-def nchw_to_nhwc(x, out=None, out_coff=0, one_minus=None):
-    """(B,C,H,W) -> NHWC (optionally into a channel slice of `out`, optionally scaled by (1 - one_minus[b,0,h,w]))."""
+def nchw_to_nhwc(x, out=None, out_coff=0, one_minus=None, dtype=None):
+    """fp32 (B,C,H,W) -> NHWC fp32 / half (optionally into a channel slice of `out`, optionally scaled by
+    (1 - one_minus[b,0,h,w]))."""
     lib = _lib.load()
+    dtype = (out.dtype if out is not None else dtype) or torch.float32
     if out is None and one_minus is None and x.dim() == 4 and x.dtype == torch.float32 and x.permute(0, 2, 3, 1).is_contiguous():
-        return x.permute(0, 2, 3, 1)          # already channels-last in memory (e.g. cuDNN NHWC output): a view, no kernel
+        v = x.permute(0, 2, 3, 1)             # already channels-last in memory (e.g. cuDNN NHWC output): a view, no kernel
+        if dtype == torch.float32:
+            return v
+        o = torch.empty(v.shape, device=x.device, dtype=torch.float16)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mr_cast_f32_to_f16(v.data_ptr(), o.data_ptr(), v.numel(), _stream(x)), "mr_cast_f32_to_f16")
+        return o
     x = x.contiguous()
     B, C, H, W = x.shape
     if out is None:
-        out = torch.empty(B, H, W, C, device=x.device, dtype=torch.float32)
+        out = torch.empty(B, H, W, C, device=x.device, dtype=dtype)
     om = one_minus.contiguous().data_ptr() if one_minus is not None else None
+    fn, name = (lib.mr_nchw_to_nhwc_f16, "mr_nchw_to_nhwc_f16") if out.dtype == torch.float16 else (lib.mr_nchw_to_nhwc, "mr_nchw_to_nhwc")
     with torch.cuda.device(x.device):
-        _lib.check(lib.mr_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), B, C, H, W, out.shape[3], out_coff, om, _stream(x)),
-                   "mr_nchw_to_nhwc")
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), B, C, H, W, out.shape[3], out_coff, om, _stream(x)), name)
     return out
 
 
 def maxpool2(x):
     lib = _lib.load()
     B, H, W, C = x.shape
-    out = torch.empty(B, H // 2, W // 2, C, device=x.device, dtype=torch.float32)
+    out = torch.empty(B, H // 2, W // 2, C, device=x.device, dtype=x.dtype)
+    fn, name = (lib.mr_maxpool2_nhwc_f16, "mr_maxpool2_nhwc_f16") if x.dtype == torch.float16 else (lib.mr_maxpool2_nhwc, "mr_maxpool2_nhwc")
     with torch.cuda.device(x.device):
-        _lib.check(lib.mr_maxpool2_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream(x)), "mr_maxpool2_nhwc")
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream(x)), name)
     return out
 
 
@@ -163,10 +184,10 @@ def max_over_frames(x, frames):
         return x
     lib = _lib.load()
     B = x.shape[0] // frames
-    out = torch.empty((B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
+    out = torch.empty((B,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    fn, name = (lib.mr_max_over_frames_f16, "mr_max_over_frames_f16") if x.dtype == torch.float16 else (lib.mr_max_over_frames, "mr_max_over_frames")
     with torch.cuda.device(x.device):
-        _lib.check(lib.mr_max_over_frames(x.data_ptr(), out.data_ptr(), frames, out.numel(), _stream(x)),
-                   "mr_max_over_frames")
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), frames, out.numel(), _stream(x)), name)
     return out
 
 
@@ -192,21 +213,23 @@ def _round_tf32(w):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def pack_tc_weight(w, src_c):
-    """Correlation kernel (Cout, Cin, kh, kw) -> [kh*kw][n_pad][k_pad] K-major, every source padded to a multiple of 32
-    channels (zero rows) and Cout padded to a multiple of 16, values rounded to TF32."""
+def pack_tc_weight(w, src_c, half=False):
+    """Correlation kernel (Cout, Cin, kh, kw) -> [kh*kw][n_pad][k_pad] K-major: every source padded to a whole number of
+    K chunks (32 fp32 / 64 half channels = one 128-byte swizzle row, zero rows), Cout padded to a multiple of 16; values
+    rounded to TF32 (fp32 storage) or converted to half."""
     Cout, Cin, kh, kw = w.shape
     assert sum(src_c) == Cin
+    kc = 2 * KC if half else KC
     n_pad = ((Cout + 15) // 16) * 16
-    k_pad = sum(((c + KC - 1) // KC) * KC for c in src_c)
+    k_pad = sum(((c + kc - 1) // kc) * kc for c in src_c)
     out = torch.zeros(kh * kw, n_pad, k_pad, device=w.device, dtype=torch.float32)
     wt = w.detach().to(torch.float32).permute(2, 3, 0, 1).reshape(kh * kw, Cout, Cin)
     ci = ko = 0
     for c in src_c:
         out[:, :Cout, ko:ko + c] = wt[:, :, ci:ci + c]
         ci += c
-        ko += ((c + KC - 1) // KC) * KC
-    return _round_tf32(out), n_pad, k_pad
+        ko += ((c + kc - 1) // kc) * kc
+    return (out.to(torch.float16).contiguous() if half else _round_tf32(out)), n_pad, k_pad
 
 
 class PackedConv:
@@ -222,23 +245,28 @@ class PackedConv:
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
         self.w32 = pack_conv_weight(w)
         self.tc_ok = allow_tc and self.cout <= 256 and self.cout >= 8 and all(c % 4 == 0 for c in self.src_c)
-        self._wtc = None
+        self.tc_ok_f16 = self.tc_ok and all(c % 8 == 0 for c in self.src_c)
+        self._wtc = {}
         self._w_src = w
 
-    def wtc(self):
-        if self._wtc is None:
-            self._wtc = pack_tc_weight(self._w_src, self.src_c)
-        return self._wtc
+    def wtc(self, half=False):
+        if half not in self._wtc:
+            self._wtc[half] = pack_tc_weight(self._w_src, self.src_c, half=half)
+        return self._wtc[half]
 
     def __call__(self, srcs, out=None, out_hw=None, final=False):
         assert tuple(s.shape[3] for s in srcs) == self.src_c, (tuple(s.shape[3] for s in srcs), self.src_c)
+        if MODE == "f16" and srcs[0].dtype == torch.float16:
+            if self.tc_ok_f16:
+                return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=False, half=True, out_f32=final)
+            assert self.cout == 1, "f16 mode: only the single-channel heads run on the CUDA-core kernel"
         if MODE == "tf32" and self.tc_ok:
             return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=not final)
         return conv2d(srcs, self.w32, self.bias, self.kh, self.kw, stride=self.stride, act=self.act, act_a=self.act_a,
                       act_b=self.act_b, out=out, pad=self.pad, out_hw=out_hw, out_step=self.out_step, out_off=self.out_off)
 
 
-def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True):
+def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f32=False):
     """Tensor-core launch (csrc/conv_tc.cu) of a PackedConv."""
     lib = _lib.load()
     x0 = srcs[0]
@@ -249,12 +277,13 @@ def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True):
         out_hw = (math.ceil(Hs / sy), math.ceil(Ws / sx))
     Ho, Wo = out_hw
     if out is None:
-        out = torch.empty(B, Ho * L.out_step[0], Wo * L.out_step[1], L.cout, device=x0.device, dtype=torch.float32)
-    wtc, n_pad, k_pad = L.wtc()
+        out = torch.empty(B, Ho * L.out_step[0], Wo * L.out_step[1], L.cout, device=x0.device,
+                          dtype=torch.float16 if (half and not out_f32) else torch.float32)
+    wtc, n_pad, k_pad = L.wtc(half)
     d = ConvDesc()
     d.n_src = len(srcs)
     for i, s in enumerate(srcs):
-        assert s.is_cuda and s.dtype == torch.float32 and s.is_contiguous()
+        assert s.is_cuda and s.dtype == (torch.float16 if half else torch.float32) and s.is_contiguous()
         assert s.shape[:3] == x0.shape[:3]
         d.src[i] = s.data_ptr()
         d.src_c[i] = s.shape[3]
@@ -267,6 +296,7 @@ def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True):
     d.dst_H, d.dst_W, d.dst_c, d.dst_coff = out.shape[1], out.shape[2], out.shape[3], 0
     d.oy_step, d.ox_step, d.oy_off, d.ox_off = L.out_step[0], L.out_step[1], L.out_off[0], L.out_off[1]
     d.act, d.act_a, d.act_b = L.act, L.act_a, L.act_b
+    d.src_dtype, d.dst_dtype = (DT_F16 if half else DT_F32), _dt(out)
     with torch.cuda.device(x0.device):
         _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
     return out
@@ -282,7 +312,7 @@ class PackedSubpixel:
     def __call__(self, srcs):
         x0 = srcs[0]
         B, Hs, Ws, _ = x0.shape
-        out = torch.empty(B, 2 * Hs, 2 * Ws, self.subs[0].cout, device=x0.device, dtype=torch.float32)
+        out = torch.empty(B, 2 * Hs, 2 * Ws, self.subs[0].cout, device=x0.device, dtype=x0.dtype)
         for L in self.subs:
             L(srcs, out=out, out_hw=(Hs, Ws))
         return out

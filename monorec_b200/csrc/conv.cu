@@ -10,6 +10,7 @@
 // Cout) through shared memory; each thread accumulates 4 pixels x TN/8 channels in registers.
 #include "mr_common.cuh"
 #include <cstdint>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -137,6 +138,14 @@ __global__ void __launch_bounds__(kConvThreads) conv2d_nhwc_kernel(const mr_conv
 // Single-output-channel layers (1x1 mask classifier, 3x3 depth heads: monorec_model.py:340-343, :521-524): a per-pixel dot
 // product, HBM-bound -- not a dense contraction, so no tensor cores and no 32-wide channel tile.  One thread per output
 // pixel, float4 channel loads (adjacent pixels are adjacent in NHWC, so a warp streams one contiguous block per filter row).
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const __half* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) conv_cout1_kernel(const mr_conv_desc d) {
     extern __shared__ float wsm[];   // [kh*kw][C]
     const int C = d.src_c[0];
@@ -156,10 +165,10 @@ __global__ void __launch_bounds__(256) conv_cout1_kernel(const mr_conv_desc d) {
         for (int kx = 0; kx < d.kw; ++kx) {
             const int ix = ox * d.sx - d.pad_l + kx;
             if (ix < 0 || ix >= d.Ws) continue;
-            const float4* p = reinterpret_cast<const float4*>(d.src[0] + (((size_t)b * d.Hs + iy) * d.Ws + ix) * C);
+            const T* p = reinterpret_cast<const T*>(d.src[0]) + (((size_t)b * d.Hs + iy) * d.Ws + ix) * C;
             const float4* w = reinterpret_cast<const float4*>(wsm + (ky * d.kw + kx) * C);
             for (int c = 0; c < C / 4; ++c) {
-                const float4 v = __ldg(p + c), q = w[c];
+                const float4 v = ld4(p + 4 * c), q = w[c];
                 acc0 = fmaf(v.x, q.x, acc0); acc1 = fmaf(v.y, q.y, acc1);
                 acc2 = fmaf(v.z, q.z, acc2); acc3 = fmaf(v.w, q.w, acc3);
             }
@@ -170,7 +179,11 @@ __global__ void __launch_bounds__(256) conv_cout1_kernel(const mr_conv_desc d) {
     d.dst[(((size_t)b * d.dst_H + dy) * d.dst_W + dx) * d.dst_c + d.dst_coff] = apply_act(v, d.act, d.act_a, d.act_b);
 }
 
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW, int dst_c,
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW, int dst_c,
                                     int dst_coff, const float* __restrict__ oms) {
     // one CTA: 32 pixels x 32 channels tile transposed through shared memory (coalesced on both sides)
     __shared__ float t[32][33];
@@ -186,7 +199,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
         if (p < HW && c < C) {
             float v = t[tx][j];
             if (oms) v *= 1.0f - __ldg(oms + (size_t)b * HW + p);
-            dst[((size_t)b * HW + p) * dst_c + dst_coff + c] = v;
+            st1(dst + ((size_t)b * HW + p) * dst_c + dst_coff + c, v);
         }
     }
 }
@@ -264,10 +277,15 @@ extern "C" int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream) {
     MR_REQUIRE(d.act >= MR_ACT_NONE && d.act <= MR_ACT_ABSTANH, "mr_conv2d_nhwc: unknown activation %d", d.act);
     if (d.Cout == 1 && d.n_src == 1 && !d.upsample2 && (d.src_c[0] % 4) == 0 && d.kh * d.kw * d.src_c[0] * 4 <= 40 * 1024) {
         const size_t total = (size_t)d.B * d.Ho * d.Wo;
-        conv_cout1_kernel<<<(unsigned)((total + 255) / 256), 256, (size_t)d.kh * d.kw * d.src_c[0] * 4, (cudaStream_t)stream>>>(d);
+        MR_REQUIRE(d.dst_dtype == MR_DT_F32, "mr_conv2d_nhwc: the single-channel heads write fp32");
+        if (d.src_dtype == MR_DT_F16)
+            conv_cout1_kernel<__half><<<(unsigned)((total + 255) / 256), 256, (size_t)d.kh * d.kw * d.src_c[0] * 4, (cudaStream_t)stream>>>(d);
+        else
+            conv_cout1_kernel<float><<<(unsigned)((total + 255) / 256), 256, (size_t)d.kh * d.kw * d.src_c[0] * 4, (cudaStream_t)stream>>>(d);
         MR_LAUNCH_CHECK("conv_cout1_kernel");
         return MR_OK;
     }
+    MR_REQUIRE(d.src_dtype == MR_DT_F32 && d.dst_dtype == MR_DT_F32, "mr_conv2d_nhwc: the CUDA-core kernel is fp32 only");
     const int tiles = ((d.Ho + kTileH - 1) / kTileH) * ((d.Wo + kTileW - 1) / kTileW);
     // the per-thread float4 weight reads need Cout-tile-aligned rows: TN=64 only when Cout is a multiple of 4
     if (d.Cout >= 64 && d.Cout % 4 == 0) {
@@ -287,8 +305,96 @@ extern "C" int mr_nchw_to_nhwc(const float* src, float* dst, int B, int C, int H
     MR_REQUIRE(dst_coff >= 0 && dst_coff + C <= dst_c, "mr_nchw_to_nhwc: channel slice out of range");
     const int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW, dst_c, dst_coff, one_minus_scale);
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(src, dst, C, HW, dst_c, dst_coff, one_minus_scale);
     MR_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_nchw_to_nhwc_f16(const float* src, void* dst, int B, int C, int H, int W, int dst_c, int dst_coff,
+                                   const float* one_minus_scale, void* stream) {
+    MR_REQUIRE(src && dst && B >= 1 && C >= 1 && H >= 1 && W >= 1, "mr_nchw_to_nhwc_f16: bad argument");
+    MR_REQUIRE(dst_coff >= 0 && dst_coff + C <= dst_c, "mr_nchw_to_nhwc_f16: channel slice out of range");
+    const int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(src, static_cast<__half*>(dst), C, HW, dst_c, dst_coff,
+                                                                          one_minus_scale);
+    MR_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+    return MR_OK;
+}
+
+namespace {
+// half NHWC twins of the pooling kernels: 8 channels (16 bytes) per thread
+__global__ void maxpool2_nhwc_f16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int C8, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int Wo = W / 2, Ho = H / 2;
+    const int c = (int)(i % C8);
+    size_t r = i / C8;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const size_t b = r / Ho;
+    const uint4* p = src + ((b * H + 2 * y) * W + 2 * x) * C8 + c;
+    uint4 q[4] = {__ldg(p), __ldg(p + C8), __ldg(p + (size_t)W * C8), __ldg(p + (size_t)W * C8 + C8)};
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __half2 a = reinterpret_cast<const __half2*>(&q[0])[k], bq = reinterpret_cast<const __half2*>(&q[1])[k];
+        const __half2 cq = reinterpret_cast<const __half2*>(&q[2])[k], dq = reinterpret_cast<const __half2*>(&q[3])[k];
+        oh[k] = __hmax2(__hmax2(a, bq), __hmax2(cq, dq));
+    }
+    dst[i] = o;
+}
+__global__ void max_over_frames_f16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int F, size_t n8) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    uint4 m = __ldg(src + i);
+    __half2* mh = reinterpret_cast<__half2*>(&m);
+    for (int f = 1; f < F; ++f) {
+        const uint4 v = __ldg(src + (size_t)f * n8 + i);
+        const __half2* vh = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mh[k] = __hmax2(mh[k], vh[k]);
+    }
+    dst[i] = m;
+}
+__global__ void cast_f32_to_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(src + i);
+    uint2 o;
+    *reinterpret_cast<__half2*>(&o.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(&o.y) = __floats2half2_rn(v.z, v.w);
+    dst[i] = o;
+}
+}  // namespace
+
+extern "C" int mr_maxpool2_nhwc_f16(const void* src, void* dst, int B, int H, int W, int C, void* stream) {
+    MR_REQUIRE(src && dst && B >= 1 && C >= 8 && (C % 8) == 0 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0,
+               "mr_maxpool2_nhwc_f16: need even H, W and C %% 8 == 0 (got H=%d W=%d C=%d)", H, W, C);
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+    maxpool2_nhwc_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(src), static_cast<uint4*>(dst), H, W, C / 8, total);
+    MR_LAUNCH_CHECK("maxpool2_nhwc_f16_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_max_over_frames_f16(const void* src, void* dst, int F, long long n_per_frame, void* stream) {
+    MR_REQUIRE(src && dst && F >= 1 && n_per_frame >= 8 && (n_per_frame % 8) == 0,
+               "mr_max_over_frames_f16: n_per_frame must be a positive multiple of 8");
+    const size_t n8 = (size_t)n_per_frame / 8;
+    max_over_frames_f16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(src), static_cast<uint4*>(dst), F, n8);
+    MR_LAUNCH_CHECK("max_over_frames_f16_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_cast_f32_to_f16(const float* src, void* dst, long long n, void* stream) {
+    MR_REQUIRE(src && dst && n >= 4 && (n % 4) == 0, "mr_cast_f32_to_f16: n must be a positive multiple of 4");
+    const size_t n4 = (size_t)n / 4;
+    cast_f32_to_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src), static_cast<uint2*>(dst), n4);
+    MR_LAUNCH_CHECK("cast_f32_to_f16_kernel");
     return MR_OK;
 }
 

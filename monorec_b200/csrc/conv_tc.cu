@@ -20,6 +20,7 @@
 #include <cuda.h>
 #include <cstdint>
 #include <cstdlib>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -40,6 +41,9 @@ struct TcArgs {
     int act;
     float act_a, act_b;
     int round_out;                 // 1: round stored activations to TF32 (nearest) so the next layer's truncation is exact
+    int kc;                        // channels per K chunk: 32 (fp32 sources, kind::tf32) or 64 (half sources, kind::f16)
+    int f16, out_f16;              // half sources+weights / half destination
+    uint32_t idesc;                // UMMA instruction descriptor
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -94,6 +98,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -119,6 +132,7 @@ __device__ __forceinline__ float act_fn(float v, int act, float a, float b) {
 // memory, activation, optional TF32 rounding, 16-byte NHWC stores.
 __device__ __forceinline__ void epilogue_row(uint32_t trow, const TcArgs& a, const float* bias_s, float* op, bool live,
                                              bool vec_ok) {
+    __half* oph = reinterpret_cast<__half*>(op);   // when a.out_f16 the caller computed `op` in half elements
     for (int n0 = 0; n0 < a.n_pad; n0 += 32) {
         uint32_t r0[16], r1[16];
         const bool second = n0 + 16 < a.n_pad;
@@ -139,7 +153,21 @@ __device__ __forceinline__ void epilogue_row(uint32_t trow, const TcArgs& a, con
                 if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
                 v[j] = x;
             }
-            if (vec_ok && nb + 16 <= a.Cout) {
+            if (a.out_f16) {
+                if (vec_ok && nb + 16 <= a.Cout) {
+                    uint4 q0, q1;
+                    __half2* h0 = reinterpret_cast<__half2*>(&q0);
+                    __half2* h1 = reinterpret_cast<__half2*>(&q1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { h0[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]); h1[j] = __floats2half2_rn(v[8 + 2 * j], v[9 + 2 * j]); }
+                    *reinterpret_cast<uint4*>(oph + nb) = q0;
+                    *reinterpret_cast<uint4*>(oph + nb + 8) = q1;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (nb + j < a.Cout) oph[nb + j] = __float2half_rn(v[j]);
+                }
+            } else if (vec_ok && nb + 16 <= a.Cout) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
@@ -218,10 +246,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 mbar_wait(empty0 + 8 * st, ph ^ 1u);
                                 const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
                                 mbar_expect_tx(full0 + 8 * st, stage_bytes);
-                                tma_load_4d(sa, tm, full0 + 8 * st, j * kKC, ix0, iy0, b);
-                                tma_load_2d(sb, &tmB, full0 + 8 * st, kbase + j * kKC, (ky * a.kw + kx) * a.n_pad);
+                                tma_load_4d(sa, tm, full0 + 8 * st, j * a.kc, ix0, iy0, b);
+                                tma_load_2d(sb, &tmB, full0 + 8 * st, kbase + j * a.kc, (ky * a.kw + kx) * a.n_pad);
                             }
-                            kbase += a.chunks[s] * kKC;
+                            kbase += a.chunks[s] * a.kc;
                         }
                     }
             }
@@ -230,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ===================== MMA issuer =====================
         // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6), a/b format TF32 = 2 @[7,10)/[10,13),
         // K-major A and B, N >> 3 @[17,23), M >> 4 @[24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = a.idesc;
         int it = 0, lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int buf = lt & 1;
@@ -246,8 +274,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
                     const uint64_t da = make_desc(sa), db = make_desc(sb);
 #pragma unroll
-                    for (int k = 0; k < kKC / 8; ++k)   // UMMA K = 8 for tf32: advance 32 bytes inside the swizzle row
-                        umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {   // UMMA K = 32 bytes (8 tf32 / 16 half): 4 steps inside the 128-byte swizzle row
+                        if (a.f16) umma_f16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
+                        else       umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
+                    }
                     umma_commit(empty0 + 8 * st);                      // frees the smem stage once these MMAs have read it
                     if (c == total - 1) umma_commit(tfull0 + 8 * buf); // accumulator complete
                 }
@@ -258,15 +288,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ===================== epilogue: TMEM -> registers -> bias/activation -> NHWC =====================
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int p = 32 * q + lane;            // pixel (= accumulator row) of this thread
-        const bool vec_ok = ((a.dst_c | a.dst_coff) & 3) == 0;
+        const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
         int lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
             const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
             const int oy = tile_y * kTileH + (p >> 4), ox = tile_x * kTileW + (p & 15);
             const bool live = (oy < a.Ho) && (ox < a.Wo);
-            float* op = a.dst + (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+            const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
                                     a.dst_c + a.dst_coff;
+            float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
             const int buf = lt & 1;
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -475,29 +506,39 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     }
     TcArgs a{};
     a.n_src = d.n_src;
+    MR_REQUIRE(d.src_dtype == MR_DT_F32 || d.src_dtype == MR_DT_F16, "mr_conv2d_nhwc_tc: bad src_dtype %d", d.src_dtype);
+    MR_REQUIRE(d.dst_dtype == MR_DT_F32 || d.dst_dtype == MR_DT_F16, "mr_conv2d_nhwc_tc: bad dst_dtype %d", d.dst_dtype);
+    const bool f16 = d.src_dtype == MR_DT_F16;
+    const int kc = f16 ? 64 : kKC;            // one 128-byte swizzle row of channels
+    const int esize = f16 ? 2 : 4;
+    const int cmult = f16 ? 8 : 4;            // pixel stride must be a multiple of 16 bytes for TMA
+    a.kc = kc; a.f16 = f16 ? 1 : 0; a.out_f16 = (d.dst_dtype == MR_DT_F16) ? 1 : 0;
+    // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6); a/b format @[7,10)/[10,13): TF32 = 2,
+    // F16 = 0; K-major A and B; N >> 3 @[17,23); M >> 4 @[24,29)
+    a.idesc = (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n_pad >> 3) << 17) | ((128u >> 4) << 24);
     int ksum = 0;
     // "halo" variant (one input box per tile, resident weights): stride 1, taps reach at most 8 px to the right, weights fit
     int chunks_all = 0;
-    for (int s = 0; s < d.n_src; ++s) chunks_all += (d.src_c[s] + kKC - 1) / kKC;
+    for (int s = 0; s < d.n_src; ++s) chunks_all += (d.src_c[s] + kc - 1) / kc;
     const size_t bres = (size_t)d.kh * d.kw * chunks_all * n_pad * 128;
     static const bool halo_enabled = (getenv("MONOREC_B200_TC_HALO") != nullptr) && (atoi(getenv("MONOREC_B200_TC_HALO")) != 0);  // experimental, off by default
-    const bool halo = halo_enabled && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7 && bres <= 112 * 1024 &&
+    const bool halo = halo_enabled && !f16 && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7 && bres <= 112 * 1024 &&
                       (210 * 1024 - ((bres + 1023) & ~size_t(1023))) / ((size_t)(16 + d.kh - 1) * kHaloPitch * 128) >= 2;
     CUtensorMap tmA[MR_CONV_MAX_SRC];
     for (int s = 0; s < d.n_src; ++s) {
         const int C = d.src_c[s];
-        MR_REQUIRE(d.src[s] != nullptr && C >= 4 && (C % 4) == 0,
-                   "mr_conv2d_nhwc_tc: source %d needs a channel count that is a multiple of 4 (got %d)", s, C);
+        MR_REQUIRE(d.src[s] != nullptr && C >= cmult && (C % cmult) == 0,
+                   "mr_conv2d_nhwc_tc: source %d needs a channel count that is a multiple of %d (got %d)", s, cmult, C);
         MR_REQUIRE((reinterpret_cast<uintptr_t>(d.src[s]) & 15) == 0, "mr_conv2d_nhwc_tc: source %d is not 16-byte aligned", s);
-        a.chunks[s] = (C + kKC - 1) / kKC;
-        ksum += a.chunks[s] * kKC;
+        a.chunks[s] = (C + kc - 1) / kc;
+        ksum += a.chunks[s] * kc;
         const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)d.Ws, (cuuint64_t)d.Hs, (cuuint64_t)d.B};
-        const cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)d.Ws * C * 4, (cuuint64_t)d.Hs * d.Ws * C * 4};
+        const cuuint64_t gstr[3] = {(cuuint64_t)C * esize, (cuuint64_t)d.Ws * C * esize, (cuuint64_t)d.Hs * d.Ws * C * esize};
         // with a traversal stride s the box spans box/s loaded elements: 16 (8) output pixels need a span of 16*s (8*s)
-        cuuint32_t box[4] = {(cuuint32_t)kKC, (cuuint32_t)(kTileW * d.sx), (cuuint32_t)(kTileH * d.sy), 1};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(kTileW * d.sx), (cuuint32_t)(kTileH * d.sy), 1};
         if (halo) { box[1] = kHaloPitch; box[2] = (cuuint32_t)(16 + d.kh - 1); }
         const cuuint32_t estr[4] = {1, (cuuint32_t)d.sx, (cuuint32_t)d.sy, 1};
-        CUresult r = encode(&tmA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.src[s]), gdim, gstr, box, estr,
+        CUresult r = encode(&tmA[s], f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.src[s]), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -511,10 +552,10 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     CUtensorMap tmB;
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)d.kh * d.kw * n_pad};
-        const cuuint64_t gstr[1] = {(cuuint64_t)k_pad * 4};
-        const cuuint32_t box[2] = {(cuuint32_t)kKC, (cuuint32_t)n_pad};
+        const cuuint64_t gstr[1] = {(cuuint64_t)k_pad * esize};
+        const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_pad};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d.weight), gdim, gstr, box, estr,
+        CUresult r = encode(&tmB, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d.weight), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {

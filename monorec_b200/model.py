@@ -62,7 +62,7 @@ class _Packed:
 
     def get(self, module, builder):
         params = list(module.parameters())
-        sig = tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
+        sig = (C.MODE,) + tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
         if sig != self.sig:
             with torch.no_grad():
                 self.data = builder()
@@ -155,7 +155,7 @@ class MaskModule(nn.Module):
         nF = len(sfcvs)
         B, D, H, W = sfcvs[0].shape
         # all frames go through the encoder as one batch of F*B volumes (the reference loops, :357-365)
-        x = torch.empty(nF * B, H, W, D, device=sfcvs[0].device, dtype=torch.float32)
+        x = torch.empty(nF * B, H, W, D, device=sfcvs[0].device, dtype=C.act_dtype())
         for f, v in enumerate(sfcvs):
             C.nchw_to_nhwc(v.to(torch.float32), out=x[f * B:(f + 1) * B])
         if not self.use_cv:
@@ -167,7 +167,7 @@ class MaskModule(nn.Module):
             for layer in P[f"enc{lvl}"]:
                 x = layer([x])
             cv_feats.append(C.max_over_frames(x, nF))
-        img = [C.nchw_to_nhwc(f.to(torch.float32)) for f in feats_nchw[:4]]
+        img = [C.nchw_to_nhwc(f.to(torch.float32), dtype=C.act_dtype()) for f in feats_nchw[:4]]
         if not self.use_features:
             img = [torch.zeros_like(t) for t in img]
         x = None
@@ -225,7 +225,7 @@ class DepthModule(nn.Module):
             return (C.PackedConv(wy, m.conv_y.bias, src_c, stride=(m.stride, 1), act=C.ACT_LEAKY, act_a=C.LEAKY_SLOPE),
                     _leaky(m.conv_x, (m.conv_x.in_channels,), stride=(1, m.stride)))
         cin0 = self._in_channels
-        self._cin0_pad = (-cin0) % 4
+        self._cin0_pad = (-cin0) % (8 if C.MODE == "f16" else 4)   # NHWC pixel stride must be a multiple of 16 bytes
         p = {"enc": []}
         for i, s in enumerate(self.enc):
             first = cr2(s[0], (cin0 + self._cin0_pad,), self._cin0_pad) if i == 0 else cr2(s[0], (e[i - 1],))
@@ -235,16 +235,16 @@ class DepthModule(nn.Module):
         p["dec2"] = (C.refine_layer(self.dec[2][0].conv2d_t, (e[2], fc[1], d[1])), cr2(self.dec[2][1], (d[2],)))
         p["dec3"] = C.refine_layer(self.dec[3].conv2d_t, (e[1], fc[0], d[2]))
         p["dec4"] = (cr2(self.dec[4][0], (e[0], d[3])), _leaky(self.dec[4][2], (d[4],)))
-        p["heads"] = [s[1] for s in self.predictors]
+        p["heads"] = [C.PackedConv(s[1].weight, s[1].bias, (s[1].in_channels,), act=C.ACT_ABSTANH, allow_tc=False)
+                      for s in self.predictors]
         return p
 
     @staticmethod
     def _cr2(srcs, pk):
         return pk[1]([pk[0](srcs)])
 
-    def _head(self, x, conv):
-        a, s = self.out_range
-        head = C.PackedConv(conv.weight, conv.bias, (conv.in_channels,), act=C.ACT_ABSTANH, act_a=a, act_b=s, allow_tc=False)
+    def _head(self, x, head):
+        head.act_a, head.act_b = self.out_range
         y = head([x], final=True)
         B, H, W, _ = y.shape
         return y.view(B, 1, H, W)
@@ -260,10 +260,10 @@ class DepthModule(nn.Module):
         # cat(cost_volume, keyframe) (:531); when MonoRecModel passes the unmasked volume plus `_cv_mask_for_depth`
         # the (1 - cv_mask) product of :713 is applied during the layout change
         cpad = self._cin0_pad
-        x = (torch.zeros if cpad else torch.empty)(B, H, W, D + 3 + cpad, device=cv.device, dtype=torch.float32)
+        x = (torch.zeros if cpad else torch.empty)(B, H, W, D + 3 + cpad, device=cv.device, dtype=C.act_dtype())
         C.nchw_to_nhwc(cv.to(torch.float32), out=x, out_coff=0, one_minus=data_dict.get("_cv_mask_for_depth"))
         C.nchw_to_nhwc(keyframe.to(torch.float32), out=x, out_coff=D)
-        img = [C.nchw_to_nhwc(f.to(torch.float32)) for f in feats_nchw[:3]]
+        img = [C.nchw_to_nhwc(f.to(torch.float32), dtype=C.act_dtype()) for f in feats_nchw[:3]]
         feats = []
         for (p0, p1) in P["enc"]:
             x = self._cr2([self._cr2([x], p0)], p1)
@@ -287,7 +287,7 @@ class DepthModule(nn.Module):
 
     def predict_depth(self, x, scale):
         """API parity with the reference (:554-557); x is NHWC inside this implementation."""
-        return self._head(x, self.predictors[scale][1])
+        return self._head(x, self._packed.get(self, self._build)["heads"][scale])
 
 
 class MonoRecModel(nn.Module):
@@ -386,11 +386,11 @@ class MonoRecModel(nn.Module):
                 data_dict["single_frame_cvs"] = [data_dict["cost_volume"].clone() for _ in data_dict["poses"]]
 
             # torchvision trunk on cuDNN: channels-last so that its outputs are already NHWC for the conv engine (the dict
-            # still holds logical (B,C,H,W) tensors); TF32 is allowed there exactly when the engine itself runs TF32
+            # still holds logical (B,C,H,W) tensors); TF32 is allowed there unless the engine runs its fp32 parity mode
             if not self._trunk_channels_last:
                 self._feature_extractor.to(memory_format=torch.channels_last)
                 self._trunk_channels_last = True
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=(C.MODE == "tf32")):
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=(C.MODE != "fp32")):
                 data_dict["image_features"] = self._feature_extractor(
                     (keyframe + .5).contiguous(memory_format=torch.channels_last))
 

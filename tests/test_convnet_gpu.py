@@ -291,3 +291,73 @@ def test_full_size_model_modes_and_graph_replay():
     print("full size tf32 vs fp32: inverse depth max|d|", dr, "mask max|d|", dm)
     assert dr < 1e-3 and dm < 5e-3
     assert res.shape == (2, 1, 256, 512) and [p.shape[-1] for p in out["predicted_inverse_depths"]] == [512, 256, 128, 64]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# half-precision storage (BASELINE config 3): tcgen05 kind::f16, half NHWC activations and weights, fp32 accumulation
+# ---------------------------------------------------------------------------------------------------------------------
+TOL_F16 = 4e-3   # half inputs/weights/outputs (10-bit mantissa each) vs fp32 reference, relative to max|ref| per layer
+
+
+@pytest.fixture
+def f16_mode():
+    from monorec_b200 import conv as C
+    old = C.MODE
+    C.set_mode("f16")
+    yield
+    C.set_mode(old)
+
+
+@pytest.mark.parametrize("cin,cout,kh,kw,sy,sx,H,W", [
+    (32, 32, 3, 3, 1, 1, 16, 32), (40, 48, 7, 1, 1, 1, 24, 40), (48, 64, 7, 1, 2, 1, 24, 40), (64, 64, 1, 7, 1, 2, 12, 40),
+    (128, 128, 1, 5, 1, 2, 10, 24), (192, 256, 3, 1, 2, 1, 18, 16), (32, 24, 3, 3, 1, 1, 9, 21), (96, 96, 3, 3, 1, 1, 7, 13)])
+def test_f16_conv_matches_torch(f16_mode, cin, cout, kh, kw, sy, sx, H, W):
+    from monorec_b200 import conv as C
+    from oracle.convnet_oracle import conv_same
+    g = torch.Generator().manual_seed(cin * 17 + cout + kw)
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5
+    b = torch.randn(cout, generator=g)
+    ref = F.leaky_relu(conv_same(x, w, b, (sy, sx)), 0.1)
+    layer = C.PackedConv(w.to(DEV), b.to(DEV), (cin,), stride=(sy, sx), act=C.ACT_LEAKY, act_a=0.1)
+    assert layer.tc_ok_f16
+    out = layer([_nhwc(x).to(DEV).half()])
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float16 and out.shape == _nhwc(ref).shape
+    assert _rel(_nchw(out.float().cpu()), ref) < TOL_F16
+
+
+def test_f16_helpers_and_subpixel(f16_mode):
+    from monorec_b200 import conv as C
+    from oracle import convnet_oracle as CO
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(4, 32, 12, 20, generator=g)
+    xh = C.nchw_to_nhwc(x.to(DEV), dtype=torch.float16)
+    assert xh.dtype == torch.float16 and torch.equal(xh.cpu(), _nhwc(x).half())
+    assert torch.equal(C.maxpool2(xh).cpu(), _nhwc(F.max_pool2d(x.half().float(), 2)).half())
+    assert torch.equal(C.max_over_frames(xh, 2).cpu(), torch.maximum(_nhwc(x).half()[:2], _nhwc(x).half()[2:]))
+    cl = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    assert torch.equal(C.nchw_to_nhwc(cl, dtype=torch.float16).cpu(), _nhwc(x).half())
+    ct = torch.nn.ConvTranspose2d(32, 48, 4, stride=2)
+    ref = CO.refine({"r.conv2d_t.weight": ct.weight.detach(), "r.conv2d_t.bias": ct.bias.detach()}, "r", x)
+    out = C.refine_layer(ct.to(DEV), (32,))([xh])
+    assert out.dtype == torch.float16 and _rel(_nchw(out.float().cpu()), ref) < TOL_F16
+    head = torch.nn.Conv2d(32, 1, 3)
+    refh = torch.abs(torch.tanh(CO.conv_same(x, head.weight.detach(), head.bias.detach())))
+    outh = C.PackedConv(head.weight.to(DEV), head.bias.to(DEV), (32,), act=C.ACT_ABSTANH, act_a=0.0, act_b=1.0, allow_tc=False)([xh], final=True)
+    assert outh.dtype == torch.float32 and _rel(_nchw(outh.cpu()), refh) < TOL_F16
+
+
+def test_full_model_f16_matches_reference_golden(f16_mode):
+    """BASELINE config 3 arithmetic on the golden model: |delta inverse depth| < 1e-3 against the fp32 reference."""
+    from monorec_b200.synthetic import make_inputs, to_device
+    from tests.helpers import GOLDEN
+    g = np.load(GOLDEN / "model_synth_small.npz")
+    B, nF, D, H, W, seed, wseed = [int(v) for v in g["cfg"]]
+    model, _ = _model_and_sd(0.7, wseed)
+    out = model(to_device(make_inputs(B, nF, H, W, seed=seed), DEV))
+    torch.cuda.synchronize()
+    dm = np.abs(out["cv_mask"].cpu().numpy() - g["g07_cv_mask"]).max()
+    dd = [np.abs(p.cpu().numpy() - g[f"g07_depth{i}"]).max() for i, p in enumerate(out["predicted_inverse_depths"])]
+    print("f16 g07 mask max|d|", dm, "depth max|d|", dd)
+    assert dm < 2e-3 and max(dd) < 1e-3
