@@ -204,6 +204,38 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
     }
 }
 
+// Half-precision fast path of the layout change (C % 32 == 0, HW % 128 == 0, 16-byte aligned channel slice): a CTA moves
+// 32 channels x 128 pixels; 128-byte coalesced reads per channel row, conflict-free shared-memory transpose (pitch 129),
+// one 16-byte store (8 channels) per thread so that a warp writes 8 pixels x 64 contiguous bytes.
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_f16_tile_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, int HW, int dst_c, int dst_coff,
+                             const float* __restrict__ oms) {
+    __shared__ float t[32][129];
+    const int b = blockIdx.z, p0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = warp; j < 32; j += 8) {
+        const float* s = src + ((size_t)b * C + c0 + j) * HW + p0 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[j][lane + 32 * k] = __ldg(s + 32 * k);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int i = threadIdx.x + 256 * r, p = i >> 2, g = i & 3;
+        uint4 q;
+        __half2* h = reinterpret_cast<__half2*>(&q);
+        if (oms) {   // same operation order as the generic kernel: v * (1 - m), then round
+            const float sc = 1.0f - __ldg(oms + (size_t)b * HW + p0 + p);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(t[8 * g + 2 * j][p] * sc, t[8 * g + 2 * j + 1][p] * sc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(t[8 * g + 2 * j][p], t[8 * g + 2 * j + 1][p]);
+        }
+        *reinterpret_cast<uint4*>(dst + ((size_t)b * HW + p0 + p) * dst_c + dst_coff + c0 + 8 * g) = q;
+    }
+}
+
 __global__ void maxpool2_nhwc_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int H, int W, int C4,
                                      size_t total) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,6 +347,13 @@ extern "C" int mr_nchw_to_nhwc_f16(const float* src, void* dst, int B, int C, in
     MR_REQUIRE(src && dst && B >= 1 && C >= 1 && H >= 1 && W >= 1, "mr_nchw_to_nhwc_f16: bad argument");
     MR_REQUIRE(dst_coff >= 0 && dst_coff + C <= dst_c, "mr_nchw_to_nhwc_f16: channel slice out of range");
     const int HW = H * W;
+    if (C % 32 == 0 && HW % 128 == 0 && dst_c % 8 == 0 && dst_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        dim3 tgrid(HW / 128, C / 32, B);
+        nchw_to_nhwc_f16_tile_kernel<<<tgrid, 256, 0, (cudaStream_t)stream>>>(src, static_cast<__half*>(dst), C, HW, dst_c, dst_coff,
+                                                                           one_minus_scale);
+        MR_LAUNCH_CHECK("nchw_to_nhwc_f16_tile_kernel");
+        return MR_OK;
+    }
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
     nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>(src, static_cast<__half*>(dst), C, HW, dst_c, dst_coff,
                                                                           one_minus_scale);

@@ -44,6 +44,7 @@ struct TcArgs {
     int kc;                        // channels per K chunk: 32 (fp32 sources, kind::tf32) or 64 (half sources, kind::f16)
     int f16, out_f16;              // half sources+weights / half destination
     uint32_t idesc;                // UMMA instruction descriptor
+    int quad;                      // 1: quad-transposed epilogue stores (64 contiguous bytes per pixel per store instruction)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -179,6 +180,87 @@ __device__ __forceinline__ void epilogue_row(uint32_t trow, const TcArgs& a, con
     }
 }
 
+__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
+    v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
+    v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
+    v.z = __shfl_xor_sync(0xffffffffu, v.z, m);
+    v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
+    return v;
+}
+// 4x4 transpose of 16-byte elements over the 4 lanes of a quad.  In: e[c] = chunk c of this lane's pixel.
+// Out: e[k] = chunk (lane & 3) of the pixel owned by lane k of the quad.
+__device__ __forceinline__ void quad_transpose(uint4 (&e)[4], int lane) {
+    const bool b0 = lane & 1, b1 = lane & 2;
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        const uint4 recv = shfl_xor_u4(b0 ? e[j] : e[j + 1], 1);
+        if (b0) e[j] = recv; else e[j + 1] = recv;
+    }
+    const uint4 r0 = shfl_xor_u4(b1 ? e[0] : e[2], 2), r1 = shfl_xor_u4(b1 ? e[1] : e[3], 2);
+    if (b1) { e[0] = r0; e[1] = r1; } else { e[2] = r0; e[3] = r1; }
+}
+
+__device__ __forceinline__ float finish(float x, const TcArgs& a) {
+    if (a.act == MR_ACT_LEAKY) x = fmaxf(x, a.act_a * x);          // slope in (0, 1)
+    else if (a.act != MR_ACT_NONE) x = act_fn(x, a.act, a.act_a, a.act_b);
+    if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    return x;
+}
+
+// Same results as epilogue_row, different store pattern: the accumulator layout gives every thread one pixel, so a plain
+// 16-byte store per thread touches 32 different pixels (half a 32-byte sector each).  Here the 4 lanes of a quad (4 adjacent
+// pixels of one output row) first transpose 4 x 16-byte chunks through shuffles, so that each store instruction writes 64
+// contiguous bytes per pixel: full sectors, a quarter of the lines per instruction.  Needs 16-byte aligned channel slices
+// and Cout a multiple of the chunk (4 floats / 8 halves); all 32 lanes must call it (shuffles), stores are predicated.
+__device__ __forceinline__ void epilogue_row_quad(uint32_t trow, const TcArgs& a, const float* bias_s, float* op, bool row_live,
+                                                  int ox, int lane) {
+    const int l = lane & 3;
+    const long pstride = (long)a.dst_c * a.ox_step;    // elements between horizontally adjacent output pixels
+    for (int n0 = 0; n0 < a.n_pad; n0 += 32) {
+        uint32_t r0[16], r1[16];
+        const bool second = n0 + 16 < a.n_pad;
+        tmem_ld16_nowait(trow + (uint32_t)n0, r0);
+        if (second) tmem_ld16_nowait(trow + (uint32_t)(n0 + 16), r1);
+        tmem_ld_wait();
+        if (a.out_f16) {
+            uint4 e[4];
+            __half2* h = reinterpret_cast<__half2*>(e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                h[j] = __floats2half2_rn(finish(__uint_as_float(r0[2 * j]) + bias_s[n0 + 2 * j], a),
+                                         finish(__uint_as_float(r0[2 * j + 1]) + bias_s[n0 + 2 * j + 1], a));
+                h[8 + j] = second ? __floats2half2_rn(finish(__uint_as_float(r1[2 * j]) + bias_s[n0 + 16 + 2 * j], a),
+                                                      finish(__uint_as_float(r1[2 * j + 1]) + bias_s[n0 + 17 + 2 * j], a))
+                                  : __floats2half2_rn(0.f, 0.f);
+            }
+            quad_transpose(e, lane);
+            const int col = n0 + 8 * l;
+            __half* base = reinterpret_cast<__half*>(op) + col;
+            const bool col_ok = row_live && (col + 8 <= a.Cout);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (col_ok && (ox - l + k) < a.Wo) *reinterpret_cast<uint4*>(base + (long)(k - l) * pstride) = e[k];
+        } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                if (hh == 1 && !second) break;
+                const int nb = n0 + 16 * hh;
+                uint4 e[4];
+                uint32_t* w = reinterpret_cast<uint32_t*>(e);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(finish(__uint_as_float(hh ? r1[j] : r0[j]) + bias_s[nb + j], a));
+                quad_transpose(e, lane);
+                const int col = nb + 4 * l;
+                float* base = op + col;
+                const bool col_ok = row_live && (col + 4 <= a.Cout);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (col_ok && (ox - l + k) < a.Wo) *reinterpret_cast<uint4*>(base + (long)(k - l) * pstride) = e[k];
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -289,6 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int p = 32 * q + lane;            // pixel (= accumulator row) of this thread
         const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
+        const bool quad_ok = vec_ok && a.quad && (a.Cout & (a.out_f16 ? 7 : 3)) == 0;
         int lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
@@ -302,7 +385,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            epilogue_row(trow, a, bias_s, op, live, vec_ok);
+            if (quad_ok) epilogue_row_quad(trow, a, bias_s, op, oy < a.Ho, ox, lane);
+            else epilogue_row(trow, a, bias_s, op, live, vec_ok);
             // hand the accumulator buffer back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -515,6 +599,8 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     a.kc = kc; a.f16 = f16 ? 1 : 0; a.out_f16 = (d.dst_dtype == MR_DT_F16) ? 1 : 0;
     // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6); a/b format @[7,10)/[10,13): TF32 = 2,
     // F16 = 0; K-major A and B; N >> 3 @[17,23); M >> 4 @[24,29)
+    static const bool kQuad = getenv("MONOREC_B200_TC_QUAD") ? (atoi(getenv("MONOREC_B200_TC_QUAD")) != 0) : true;   // epilogue store pattern
+    a.quad = kQuad ? 1 : 0;
     a.idesc = (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n_pad >> 3) << 17) | ((128u >> 4) << 24);
     int ksum = 0;
     // "halo" variant (one input box per tile, resident weights): stride 1, taps reach at most 8 px to the right, weights fit

@@ -97,8 +97,52 @@ class ResnetEncoder(nn.Module):
                 weights = w
         self.encoder = torchvision.models.resnet18(weights=weights)
 
+    # ---- inference fast path: BatchNorm (eval mode = a fixed per-channel affine) folded into the preceding convolution ----
+    @staticmethod
+    def _fold(conv, bn):
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        w = (conv.weight * scale.view(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+        b = bn.bias - bn.running_mean * scale
+        if conv.bias is not None:
+            b = b + conv.bias * scale
+        return w, b.contiguous()
+
+    def _folded(self):
+        e = self.encoder
+        tensors = [t for n, t in list(e.named_parameters()) + list(e.named_buffers()) if not n.startswith("fc.")]
+        sig = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
+        if sig != getattr(self, "_fold_sig", None):
+            with torch.no_grad():
+                f = {"stem": self._fold(e.conv1, e.bn1), "blocks": []}
+                for layer in (e.layer1, e.layer2, e.layer3, e.layer4):
+                    blocks = []
+                    for blk in layer:
+                        down = None if blk.downsample is None else self._fold(blk.downsample[0], blk.downsample[1]) + (
+                            blk.downsample[0].stride,)
+                        blocks.append((self._fold(blk.conv1, blk.bn1), blk.conv1.stride, self._fold(blk.conv2, blk.bn2), down))
+                    f["blocks"].append(blocks)
+            self._fold_cache, self._fold_sig = f, sig
+        return self._fold_cache
+
+    def _forward_folded(self, input_image):
+        import torch.nn.functional as F
+        e, f = self.encoder, self._folded()
+        x = (input_image - 0.45) / 0.225
+        x = F.conv2d(x, *f["stem"], stride=e.conv1.stride, padding=e.conv1.padding).relu_()
+        self.features = [x]
+        x = e.maxpool(x)
+        for blocks in f["blocks"]:
+            for (w1, b1), stride, (w2, b2), down in blocks:
+                idt = x if down is None else F.conv2d(x, down[0], down[1], stride=down[2])
+                out = F.conv2d(x, w1, b1, stride=stride, padding=1).relu_()
+                x = F.conv2d(out, w2, b2, padding=1).add_(idt).relu_()
+            self.features.append(x)
+        return self.features
+
     def forward(self, input_image):
         e = self.encoder
+        if not e.training and not torch.is_grad_enabled():
+            return self._forward_folded(input_image)
         x = (input_image - 0.45) / 0.225
         self.features = [e.relu(e.bn1(e.conv1(x)))]
         self.features.append(e.layer1(e.maxpool(self.features[-1])))

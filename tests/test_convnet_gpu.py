@@ -338,6 +338,13 @@ def test_f16_helpers_and_subpixel(f16_mode):
     assert torch.equal(C.max_over_frames(xh, 2).cpu(), torch.maximum(_nhwc(x).half()[:2], _nhwc(x).half()[2:]))
     cl = x.to(DEV).contiguous(memory_format=torch.channels_last)
     assert torch.equal(C.nchw_to_nhwc(cl, dtype=torch.float16).cpu(), _nhwc(x).half())
+    # tiled fast path (C % 32 == 0, H*W % 128 == 0): plain, and into a channel slice with the (1 - mask) product
+    y = torch.randn(3, 64, 16, 24, generator=g)
+    m = torch.rand(3, 1, 16, 24, generator=g)
+    assert torch.equal(C.nchw_to_nhwc(y.to(DEV), dtype=torch.float16).cpu(), _nhwc(y).half())
+    buf = torch.zeros(3, 16, 24, 72, device=DEV, dtype=torch.float16)
+    C.nchw_to_nhwc(y.to(DEV), out=buf, out_coff=8, one_minus=m.to(DEV))
+    assert torch.equal(buf[..., 8:].cpu(), _nhwc(y * (1.0 - m)).half()) and float(buf[..., :8].abs().max()) == 0.0
     ct = torch.nn.ConvTranspose2d(32, 48, 4, stride=2)
     ref = CO.refine({"r.conv2d_t.weight": ct.weight.detach(), "r.conv2d_t.bias": ct.bias.detach()}, "r", x)
     out = C.refine_layer(ct.to(DEV), (32,))([xh])

@@ -62,3 +62,33 @@ def test_unsupported_reference_options_raise():
     assert hasattr(m, "att_module") and not hasattr(m, "depth_module")
     m = MonoRecModel(pretrain_mode=1)
     assert hasattr(m, "depth_module") and not hasattr(m, "att_module")
+
+
+def test_trunk_batchnorm_folding_matches_unfolded_eval():
+    """ResnetEncoder's inference path folds eval-mode BatchNorm into the convolutions (monorec_model.py:118-129 semantics);
+    the folded copy must track parameter updates."""
+    from monorec_b200.model import ResnetEncoder
+    torch.manual_seed(0)
+    enc = ResnetEncoder(18, pretrained=False).eval()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.5)
+            m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    x = torch.rand(2, 3, 64, 128)
+    with torch.enable_grad():
+        ref = [t.detach().clone() for t in enc(x)]          # module-by-module path
+    with torch.no_grad():
+        out = [t.clone() for t in enc(x)]                    # folded path
+    assert len(out) == 5
+    for a, b in zip(ref, out):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
+    sd = {k: v.clone() for k, v in enc.state_dict().items()}
+    sd["encoder.bn1.bias"] += 1.0
+    enc.load_state_dict(sd)
+    with torch.no_grad():
+        out2 = enc(x)[0]
+    with torch.enable_grad():
+        ref2 = enc(x)[0].detach()
+    assert float((out2 - ref2).abs().max()) < 1e-4 and float((out2 - out[0]).abs().max()) > 0.5

@@ -5,8 +5,8 @@ timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest.log 2>&1; tail
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $? lines $(wc -l < gpurun_out/bench.json)"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null; cut -c1-160 gpurun_out/bench_ref.json
+for m in tf32 f16; do echo -n "$m: "; MONOREC_B200_CONV=$m timeout 300 python tools/profile_model.py 8 4 10 2>&1 | tail -1; done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 6 -c 40 --csv --log-file gpurun_out/bench_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-full-model > gpurun_out/ncu_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:cost_volume -s 2 -c 1 -o gpurun_out/prof_k1_final python tools/profile_cv.py > gpurun_out/ncu_k1.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 2 -c 1 -o gpurun_out/prof_k2_final python tools/profile_conv.py > gpurun_out/ncu_k2.log 2>&1
-MONOREC_B200_CONV=tf32 timeout 600 python tools/profile_model.py 8 4 3 2>&1 | tail -1
+MONOREC_B200_CONV=f16 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 2 -c 1 -o gpurun_out/prof_k2_f16 python tools/profile_conv.py > gpurun_out/ncu_k2.log 2>&1
+MONOREC_B200_CONV=f16 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/model_launches_f16.csv python tools/profile_model.py 8 4 1 > gpurun_out/ncu_model_f16.log 2>&1
 cat gpurun_out/bench.json | cut -c1-200
