@@ -23,6 +23,9 @@ KC = 32            # channels per K chunk of the tensor-core kernel (csrc/conv_t
 # "f16" = tcgen05 kind::f16 with half NHWC activations and weights (fp32 accumulate; BASELINE config 3),
 # "fp32" = CUDA-core FMA kernel (bit-level parity path).  1-channel heads always use the CUDA-core dot-product kernel.
 MODE = os.environ.get("MONOREC_B200_CONV", "tf32").lower()
+# half sources: allow 32-channel K chunks (SWIZZLE_64B rows); off when the halo kernel is enabled for half layers, which
+# needs 128-byte rows (csrc/conv_tc.cu)
+K32 = os.environ.get("MONOREC_B200_TC_K32", "1") != "0" and os.environ.get("MONOREC_B200_TC_HALO_F16", "0") == "0"
 DT_F32, DT_F16 = 0, 1
 
 
@@ -215,11 +218,15 @@ def _round_tf32(w):
 
 def pack_tc_weight(w, src_c, half=False):
     """Correlation kernel (Cout, Cin, kh, kw) -> [kh*kw][n_pad][k_pad] K-major: every source padded to a whole number of
-    K chunks (32 fp32 / 64 half channels = one 128-byte swizzle row, zero rows), Cout padded to a multiple of 16; values
+    K chunks (32 fp32 / 64 half channels = one 128-byte swizzle row, or 32 half channels = one 64-byte row when that pads
+    less; zero rows), Cout padded to a multiple of 16; values
     rounded to TF32 (fp32 storage) or converted to half."""
     Cout, Cin, kh, kw = w.shape
     assert sum(src_c) == Cin
     kc = 2 * KC if half else KC
+    if half and K32 and all(c <= 32 for c in src_c):
+        kc = 32   # sources of <= 32 channels: 64-byte swizzle rows instead of half-empty 128-byte ones (same number of K
+        #           chunks, half the TMA and MMA work per chunk); the library reads the chunk width off k_pad
     n_pad = ((Cout + 15) // 16) * 16
     k_pad = sum(((c + kc - 1) // kc) * kc for c in src_c)
     out = torch.zeros(kh * kw, n_pad, k_pad, device=w.device, dtype=torch.float32)

@@ -45,6 +45,8 @@ struct TcArgs {
     int f16, out_f16;              // half sources+weights / half destination
     uint32_t idesc;                // UMMA instruction descriptor
     int quad;                      // 1: quad-transposed epilogue stores (64 contiguous bytes per pixel per store instruction)
+    int row_bytes;                 // bytes of one K chunk row in shared memory = swizzle span: 128, or 64 (half sources, 32-channel chunks)
+    uint64_t desc_hi;              // smem descriptor without the start address (LBO, SBO = 8 rows, version, swizzle mode)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -278,8 +280,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
-    const uint32_t stage_bytes = kABytes + b_bytes;
+    const uint32_t a_bytes = 128u * (uint32_t)a.row_bytes, b_bytes = (uint32_t)a.n_pad * (uint32_t)a.row_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
     const int stages = a.stages;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
     const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
@@ -326,7 +328,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 const int st = it % stages;
                                 const uint32_t ph = (uint32_t)(it / stages) & 1u;
                                 mbar_wait(empty0 + 8 * st, ph ^ 1u);
-                                const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
+                                const uint32_t sa = tile_base + st * stage_bytes, sb = sa + a_bytes;
                                 mbar_expect_tx(full0 + 8 * st, stage_bytes);
                                 tma_load_4d(sa, tm, full0 + 8 * st, j * a.kc, ix0, iy0, b);
                                 tma_load_2d(sb, &tmB, full0 + 8 * st, kbase + j * a.kc, (ky * a.kw + kx) * a.n_pad);
@@ -353,10 +355,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 mbar_wait(full0 + 8 * st, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t sa = tile_base + st * stage_bytes, sb = sa + kABytes;
-                    const uint64_t da = make_desc(sa), db = make_desc(sb);
+                    const uint32_t sa = tile_base + st * stage_bytes, sb = sa + a_bytes;
+                    const uint64_t da = (uint64_t)((sa & 0x3FFFF) >> 4) | a.desc_hi, db = (uint64_t)((sb & 0x3FFFF) >> 4) | a.desc_hi;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {   // UMMA K = 32 bytes (8 tf32 / 16 half): 4 steps inside the 128-byte swizzle row
+                    for (int k = 0; k < 4; ++k) {   // UMMA K = 32 bytes (8 tf32 / 16 half): 4 (2) steps inside the 128 (64)-byte swizzle row
+                        if (32 * k >= a.row_bytes) break;
                         if (a.f16) umma_f16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
                         else       umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
                     }
@@ -471,7 +474,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_expect_tx(bfull, bres_bytes);
             for (int tp = 0; tp < taps; ++tp)
                 for (int cg = 0; cg < chunks_per_tap; ++cg)
-                    tma_load_2d(base + (uint32_t)(tp * chunks_per_tap + cg) * b_bytes, &tmB, bfull, cg * kKC, tp * a.n_pad);
+                    tma_load_2d(base + (uint32_t)(tp * chunks_per_tap + cg) * b_bytes, &tmB, bfull, cg * a.kc, tp * a.n_pad);
             int it = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
                 const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
@@ -484,14 +487,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const uint32_t ph = (uint32_t)(it / stages) & 1u;
                         mbar_wait(aempty0 + 8 * st, ph ^ 1u);
                         mbar_expect_tx(afull0 + 8 * st, a_bytes);
-                        tma_load_4d(a_base + st * a_bytes, tm, afull0 + 8 * st, j * kKC, ix0, iy0, b);
+                        tma_load_4d(a_base + st * a_bytes, tm, afull0 + 8 * st, j * a.kc, ix0, iy0, b);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = a.idesc;
         mbar_wait(bfull, 0);
         int it = 0, lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
@@ -511,8 +514,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             const uint64_t da = make_desc_halo(sa + (uint32_t)(ky * kHaloPitch + kx) * 128u);
                             const uint64_t db = make_desc(base + (uint32_t)((ky * a.kw + kx) * chunks_per_tap + cg) * b_bytes);
 #pragma unroll
-                            for (int k = 0; k < kKC / 8; ++k)
-                                umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per 128-byte row (8 tf32 / 16 half each)
+                                if (a.f16) umma_f16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
+                                else       umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
+                            }
                         }
                     umma_commit(aempty0 + 8 * st);
                     if (cg == chunks_per_tap - 1) umma_commit(tfull0 + 8 * buf);
@@ -524,20 +529,23 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         // ===================== epilogue (tile = 16 rows x 8 columns) =====================
         const int q = warp & 3;
         const int p = 32 * q + lane;
-        const bool vec_ok = ((a.dst_c | a.dst_coff) & 3) == 0;
+        const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
+        const bool quad_ok = vec_ok && a.quad && (a.Cout & (a.out_f16 ? 7 : 3)) == 0;
         int lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
             const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
             const int oy = tile_y * 16 + (p >> 3), ox = tile_x * 8 + (p & 7);
             const bool live = (oy < a.Ho) && (ox < a.Wo);
-            float* op = a.dst + (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+            const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
                                     a.dst_c + a.dst_coff;
+            float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
             const int buf = lt & 1;
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            epilogue_row(trow, a, bias_s, op, live, vec_ok);
+            if (quad_ok) epilogue_row_quad(trow, a, bias_s, op, oy < a.Ho, ox, lane);
+            else epilogue_row(trow, a, bias_s, op, live, vec_ok);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -593,9 +601,20 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     MR_REQUIRE(d.src_dtype == MR_DT_F32 || d.src_dtype == MR_DT_F16, "mr_conv2d_nhwc_tc: bad src_dtype %d", d.src_dtype);
     MR_REQUIRE(d.dst_dtype == MR_DT_F32 || d.dst_dtype == MR_DT_F16, "mr_conv2d_nhwc_tc: bad dst_dtype %d", d.dst_dtype);
     const bool f16 = d.src_dtype == MR_DT_F16;
-    const int kc = f16 ? 64 : kKC;            // one 128-byte swizzle row of channels
+    // K chunk = one swizzle row of channels: 32 fp32 or 64 half (128 bytes).  Half sources whose channel counts waste less
+    // with 32-channel chunks (32, 96, ... channels) are packed that way by the caller (k_pad tells): 64-byte rows, SWIZZLE_64B,
+    // so that neither TMA nor the MMA spends time on the zero half of a 128-byte row.
+    int kc = f16 ? 64 : kKC;
+    if (f16) {
+        int k64 = 0, k32 = 0;
+        for (int s = 0; s < d.n_src; ++s) { k64 += (d.src_c[s] + 63) / 64 * 64; k32 += (d.src_c[s] + 31) / 32 * 32; }
+        if (k_pad != k64 && k_pad == k32) kc = 32;
+    }
     const int esize = f16 ? 2 : 4;
     const int cmult = f16 ? 8 : 4;            // pixel stride must be a multiple of 16 bytes for TMA
+    a.row_bytes = kc * (f16 ? 2 : 4);
+    a.desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((8 * a.row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) |
+                ((uint64_t)(a.row_bytes == 128 ? 2 : 4) << 61);   // layout: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     a.kc = kc; a.f16 = f16 ? 1 : 0; a.out_f16 = (d.dst_dtype == MR_DT_F16) ? 1 : 0;
     // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6); a/b format @[7,10)/[10,13): TF32 = 2,
     // F16 = 0; K-major A and B; N >> 3 @[17,23); M >> 4 @[24,29)
@@ -607,9 +626,26 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     int chunks_all = 0;
     for (int s = 0; s < d.n_src; ++s) chunks_all += (d.src_c[s] + kc - 1) / kc;
     const size_t bres = (size_t)d.kh * d.kw * chunks_all * n_pad * 128;
-    static const bool halo_enabled = (getenv("MONOREC_B200_TC_HALO") != nullptr) && (atoi(getenv("MONOREC_B200_TC_HALO")) != 0);  // experimental, off by default
-    const bool halo = halo_enabled && !f16 && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7 && bres <= 112 * 1024 &&
-                      (210 * 1024 - ((bres + 1023) & ~size_t(1023))) / ((size_t)(16 + d.kh - 1) * kHaloPitch * 128) >= 2;
+    // MONOREC_B200_TC_HALO: unset = automatic, 0 = never, 1 / 2 = always when eligible with that many CTAs per SM.
+    // Automatic (measured on the stacks' layers): two CTAs per SM whenever weights + two halo stages fit twice; one CTA per
+    // SM for the other 3x3 layers whose weights fit; the tap-refetch kernel for everything else.
+    static const int halo_env = getenv("MONOREC_B200_TC_HALO") ? atoi(getenv("MONOREC_B200_TC_HALO")) : -1;
+    static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : false;
+    const size_t halo_a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * 128;
+    const size_t bres_al = (bres + 1023) & ~size_t(1023);
+    auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights (228 KB per SM, 1 KB reserved + ~1.1 KB static per CTA)
+        const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas;
+        int st = bres_al + 2048 < budget ? (int)((budget - 2048 - bres_al) / halo_a_bytes) : 0;
+        return st > 4 ? 4 : st;
+    };
+    int halo_ctas = 0;
+    if (halo_env != 0 && (!f16 || halo_f16) && a.row_bytes == 128 && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
+        if (halo_env == 1 || halo_env == 2) halo_ctas = halo_fit(halo_env) >= 2 ? halo_env : 0;
+        else if (halo_fit(2) >= 2) halo_ctas = 2;
+        else if (d.kh == 3 && d.kw == 3 && halo_fit(1) >= 2) halo_ctas = 1;
+    }
+    const bool halo = halo_ctas > 0;
+    const int halo_stages = halo ? halo_fit(halo_ctas) : 0;
     CUtensorMap tmA[MR_CONV_MAX_SRC];
     for (int s = 0; s < d.n_src; ++s) {
         const int C = d.src_c[s];
@@ -625,8 +661,8 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         if (halo) { box[1] = kHaloPitch; box[2] = (cuuint32_t)(16 + d.kh - 1); }
         const cuuint32_t estr[4] = {1, (cuuint32_t)d.sx, (cuuint32_t)d.sy, 1};
         CUresult r = encode(&tmA[s], f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.src[s]), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             mr::set_error("mr_conv2d_nhwc_tc: cuTensorMapEncodeTiled(A%d) failed with CUresult %d", s, (int)r);
             return MR_EINVAL;
@@ -642,8 +678,8 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_pad};
         const cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&tmB, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d.weight), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             mr::set_error("mr_conv2d_nhwc_tc: cuTensorMapEncodeTiled(B) failed with CUresult %d", (int)r);
             return MR_EINVAL;
@@ -653,7 +689,7 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     a.Ho = d.Ho; a.Wo = d.Wo; a.Cout = d.Cout; a.n_pad = n_pad;
     a.tiles_x = halo ? (d.Wo + 7) / 8 : (d.Wo + kTileW - 1) / kTileW;
     const int tiles = a.tiles_x * (halo ? (d.Ho + 15) / 16 : (d.Ho + kTileH - 1) / kTileH);
-    const size_t stage_bytes = (size_t)kABytes + (size_t)n_pad * 128;
+    const size_t stage_bytes = (size_t)(128 + n_pad) * a.row_bytes;
     a.tiles_per_img = tiles;
     a.total_tiles = tiles * d.B;
     // persistent grid: two CTAs per SM when two double-buffered accumulators fit TMEM (2 x 2 x n_pad <= 512 columns),
@@ -682,20 +718,14 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     a.oy_step = d.oy_step; a.ox_step = d.ox_step; a.oy_off = d.oy_off; a.ox_off = d.ox_off;
     a.act = d.act; a.act_a = d.act_a; a.act_b = d.act_b; a.round_out = round_out;
     if (halo) {
-        const size_t a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * 128;
-        const size_t bres_al = (bres + 1023) & ~size_t(1023);
-        int st = (int)((210 * 1024 - bres_al) / a_bytes);
-        if (st > 4) st = 4;
-        if (st >= 2) {
-            a.stages = st;
-            const size_t smem = bres_al + (size_t)st * a_bytes + 1024;
-            MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-            int grid = sms;
-            if (grid > a.total_tiles) grid = a.total_tiles;
-            conv_tc_halo_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
-            MR_LAUNCH_CHECK("conv_tc_halo_kernel");
-            return MR_OK;
-        }
+        a.stages = halo_stages;
+        const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
+        MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+        int grid = sms * halo_ctas;
+        if (grid > a.total_tiles) grid = a.total_tiles;
+        conv_tc_halo_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+        MR_LAUNCH_CHECK("conv_tc_halo_kernel");
+        return MR_OK;
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));

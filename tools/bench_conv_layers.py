@@ -7,7 +7,11 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from monorec_b200 import conv as C  # noqa: E402
 
-C.set_mode("tf32")
+import os  # noqa: E402
+
+MODE = os.environ.get("MONOREC_B200_CONV", "tf32")
+C.set_mode(MODE)
+half = MODE == "f16"
 dev = "cuda:0"
 torch.manual_seed(0)
 
@@ -26,7 +30,7 @@ def timed(fn, n=10):
 
 
 cases = [("mask enc0 3x3 32->32 B32 full", 32, 256, 512, (32,), 32, 3, 3),
-         ("depth enc0 7x1 36->48 B8 full", 8, 256, 512, (36,), 48, 7, 1),
+         ("depth enc0 7x1 40->48 B8 full", 8, 256, 512, (40,), 48, 7, 1),
          ("depth enc0 1x7 48->48 B8 full", 8, 256, 512, (48,), 48, 1, 7),
          ("mask dec3.2 3x3 48->48 B8 full", 8, 256, 512, (48,), 48, 3, 3),
          ("mask dec3.1 3x3 32+64->48 B8 full", 8, 256, 512, (32, 64), 48, 3, 3),
@@ -34,9 +38,11 @@ cases = [("mask enc0 3x3 32->32 B32 full", 32, 256, 512, (32,), 32, 3, 3),
          ("mask dec1.1 3x3 64+64+96->96 B8 1/4", 8, 64, 128, (64, 64, 96), 96, 3, 3)]
 for name, B, H, W, src_c, cout, kh, kw in cases:
     xs = [torch.randn(B, H, W, c, device=dev) for c in src_c]
+    if half:
+        xs = [x.half() for x in xs]
     conv = torch.nn.Conv2d(sum(src_c), cout, (kh, kw)).to(dev)
     L = C.PackedConv(conv.weight, conv.bias, src_c, act=C.ACT_LEAKY, act_a=0.1)
     us = timed(lambda: L(xs))
     flops = 2.0 * B * H * W * sum(src_c) * cout * kh * kw
-    byts = 4.0 * B * H * W * (sum(src_c) + cout)
+    byts = (2.0 if half else 4.0) * B * H * W * (sum(src_c) + cout)
     print(f"{name:40s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {byts / us / 1e3:7.1f} GB/s (in+out)")
