@@ -23,9 +23,10 @@ KC = 32            # channels per K chunk of the tensor-core kernel (csrc/conv_t
 # "f16" = tcgen05 kind::f16 with half NHWC activations and weights (fp32 accumulate; BASELINE config 3),
 # "fp32" = CUDA-core FMA kernel (bit-level parity path).  1-channel heads always use the CUDA-core dot-product kernel.
 MODE = os.environ.get("MONOREC_B200_CONV", "tf32").lower()
-# half sources: allow 32-channel K chunks (SWIZZLE_64B rows); off when the halo kernel is enabled for half layers, which
-# needs 128-byte rows (csrc/conv_tc.cu)
-K32 = os.environ.get("MONOREC_B200_TC_K32", "1") != "0" and os.environ.get("MONOREC_B200_TC_HALO_F16", "0") == "0"
+# half sources of <= 32 channels: 32-channel K chunks (SWIZZLE_64B rows).  Stride-1 layers of that kind go to the halo kernel
+# instead (csrc/conv_tc.cu, faster still), which needs 128-byte rows, unless MONOREC_B200_TC_HALO_F16=0 / MONOREC_B200_TC_HALO=0.
+K32 = os.environ.get("MONOREC_B200_TC_K32", "1") != "0"
+HALO_F16 = os.environ.get("MONOREC_B200_TC_HALO_F16", "1") != "0" and os.environ.get("MONOREC_B200_TC_HALO", "") != "0"
 DT_F32, DT_F16 = 0, 1
 
 
@@ -216,7 +217,7 @@ def _round_tf32(w):
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def pack_tc_weight(w, src_c, half=False):
+def pack_tc_weight(w, src_c, half=False, allow_k32=True):
     """Correlation kernel (Cout, Cin, kh, kw) -> [kh*kw][n_pad][k_pad] K-major: every source padded to a whole number of
     K chunks (32 fp32 / 64 half channels = one 128-byte swizzle row, or 32 half channels = one 64-byte row when that pads
     less; zero rows), Cout padded to a multiple of 16; values
@@ -224,7 +225,7 @@ def pack_tc_weight(w, src_c, half=False):
     Cout, Cin, kh, kw = w.shape
     assert sum(src_c) == Cin
     kc = 2 * KC if half else KC
-    if half and K32 and all(c <= 32 for c in src_c):
+    if half and K32 and allow_k32 and all(c <= 32 for c in src_c):
         kc = 32   # sources of <= 32 channels: 64-byte swizzle rows instead of half-empty 128-byte ones (same number of K
         #           chunks, half the TMA and MMA work per chunk); the library reads the chunk width off k_pad
     n_pad = ((Cout + 15) // 16) * 16
@@ -258,7 +259,8 @@ class PackedConv:
 
     def wtc(self, half=False):
         if half not in self._wtc:
-            self._wtc[half] = pack_tc_weight(self._w_src, self.src_c, half=half)
+            self._wtc[half] = pack_tc_weight(self._w_src, self.src_c, half=half,
+                                             allow_k32=not (HALO_F16 and tuple(self.stride) == (1, 1)))
         return self._wtc[half]
 
     def __call__(self, srcs, out=None, out_hw=None, final=False):

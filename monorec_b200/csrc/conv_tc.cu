@@ -627,10 +627,11 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     for (int s = 0; s < d.n_src; ++s) chunks_all += (d.src_c[s] + kc - 1) / kc;
     const size_t bres = (size_t)d.kh * d.kw * chunks_all * n_pad * 128;
     // MONOREC_B200_TC_HALO: unset = automatic, 0 = never, 1 / 2 = always when eligible with that many CTAs per SM.
-    // Automatic (measured on the stacks' layers): two CTAs per SM whenever weights + two halo stages fit twice; one CTA per
-    // SM for the other 3x3 layers whose weights fit; the tap-refetch kernel for everything else.
+    // Automatic (measured on the stacks' layers): only when weights + two halo stages fit twice per SM, i.e. two CTAs per
+    // SM (32->32 3x3 over the single-frame volumes: 631 -> 452 us in TF32, 489 -> 429 us in half); with a single CTA per SM
+    // its four epilogue warps become the bottleneck (48->48 3x3: 300 -> 335 us), so those layers keep the tap-refetch kernel.
     static const int halo_env = getenv("MONOREC_B200_TC_HALO") ? atoi(getenv("MONOREC_B200_TC_HALO")) : -1;
-    static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : false;
+    static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : true;
     const size_t halo_a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * 128;
     const size_t bres_al = (bres + 1023) & ~size_t(1023);
     auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights (228 KB per SM, 1 KB reserved + ~1.1 KB static per CTA)
@@ -642,7 +643,6 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     if (halo_env != 0 && (!f16 || halo_f16) && a.row_bytes == 128 && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
         if (halo_env == 1 || halo_env == 2) halo_ctas = halo_fit(halo_env) >= 2 ? halo_env : 0;
         else if (halo_fit(2) >= 2) halo_ctas = 2;
-        else if (d.kh == 3 && d.kw == 3 && halo_fit(1) >= 2) halo_ctas = 1;
     }
     const bool halo = halo_ctas > 0;
     const int halo_stages = halo ? halo_fit(halo_ctas) : 0;
