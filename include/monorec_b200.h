@@ -141,8 +141,12 @@ int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
  * `weight` is packed as [kh*kw][n_pad][k_pad] (K contiguous): Cout padded to n_pad (multiple of 16, <= 256), every source
  * padded to a multiple of 32 channels (k_pad = sum).  Needs src_c[i] % 4 == 0 and upsample2 == 0 (nearest-x2 upsampling is
  * expressed as sub-pixel convolutions on this path).  round_out: round stored activations to TF32 (nearest).
- * With src_dtype = MR_DT_F16 the sources and the packed weights are half, a K chunk is 64 channels (k_pad counts 64s) and
- * the MMA is kind::f16; dst_dtype selects half or float output. */
+ * With src_dtype = MR_DT_F16 the sources and the packed weights are half, a K chunk is 64 channels (every source padded to
+ * a multiple of 64) or, if the caller packed every source to a multiple of 32 instead and that gives a different k_pad,
+ * 32 channels (64-byte swizzle rows); the MMA is kind::f16; dst_dtype selects half or float output.
+ * Stride-1 layers whose packed weights fit in shared memory twice per SM run on the "halo" variant of the kernel (same
+ * results).  Tuning switches (environment, read once): MONOREC_B200_TC_HALO=0|1|2, MONOREC_B200_TC_HALO_F16=0|1,
+ * MONOREC_B200_TC_QUAD=0|1, MONOREC_B200_TC_CTAS=n. */
 int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream);
 /* sizeof(mr_conv_desc) as compiled into the library (bindings check their mirror of the struct against it). */
 int mr_sizeof_conv_desc(void);

@@ -27,6 +27,7 @@ MODE = os.environ.get("MONOREC_B200_CONV", "tf32").lower()
 # instead (csrc/conv_tc.cu, faster still), which needs 128-byte rows, unless MONOREC_B200_TC_HALO_F16=0 / MONOREC_B200_TC_HALO=0.
 K32 = os.environ.get("MONOREC_B200_TC_K32", "1") != "0"
 HALO_F16 = os.environ.get("MONOREC_B200_TC_HALO_F16", "1") != "0" and os.environ.get("MONOREC_B200_TC_HALO", "") != "0"
+HALO_K32 = os.environ.get("MONOREC_B200_TC_HALO_K32", "0") != "0"   # experimental: 64-byte rows inside the halo box as well
 DT_F32, DT_F16 = 0, 1
 
 
@@ -260,7 +261,7 @@ class PackedConv:
     def wtc(self, half=False):
         if half not in self._wtc:
             self._wtc[half] = pack_tc_weight(self._w_src, self.src_c, half=half,
-                                             allow_k32=not (HALO_F16 and tuple(self.stride) == (1, 1)))
+                                             allow_k32=HALO_K32 or not (HALO_F16 and tuple(self.stride) == (1, 1)))
         return self._wtc[half]
 
     def __call__(self, srcs, out=None, out_hw=None, final=False):

@@ -12,7 +12,11 @@
 //   * both land in 128-byte-swizzled K-major shared-memory tiles that tcgen05.mma consumes through smem descriptors.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
 // warps 2..5 = epilogue (tcgen05.ld -> bias -> activation -> NHWC store, optional sub-pixel placement).
-// Pipelines: smem full/empty mbarrier ring between TMA and MMA; one tmem-full mbarrier between MMA and epilogue.
+// Pipelines: smem full/empty mbarrier ring between TMA and MMA; tmem full/empty mbarriers between MMA and epilogue (the
+// accumulator is double-buffered in TMEM, the kernel is persistent over output tiles).
+// Variants chosen by the host code at the bottom of this file: 64-byte swizzle rows for half sources of <= 32 channels;
+// epilogue stores transposed across lane quads (full 32-byte sectors); conv_tc_halo_kernel (resident weights, one input
+// box per tile) for stride-1 layers whose weights fit in shared memory twice per SM.
 //
 // Reference being replaced: nn.Conv2d / nn.ConvTranspose2d + bias + LeakyReLU of model/layers.py:289-400 as used by
 // MaskModule / DepthModule (model/monorec/monorec_model.py:287-385, :476-557).
@@ -27,7 +31,6 @@ namespace {
 constexpr int kTcThreads = 192;
 constexpr int kKC = 32;                 // fp32 channels per K chunk = one 128-byte swizzle row
 constexpr int kTileH = 8, kTileW = 16;  // 128 output pixels per CTA
-constexpr uint32_t kABytes = 128 * 128; // A stage: 128 rows x 128 B
 
 struct TcArgs {
     int n_src;
@@ -85,13 +88,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major) |
-//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
+//   [32,46) stride byte offset >> 4 (distance between 8-row groups) | [46,48) version = 1 | [49,52) base offset |
+//   [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.  Everything but the start address is layer-constant: TcArgs::desc_hi.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -418,10 +418,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #endif
 constexpr int kHaloPitch = 16;   // pixels per halo row in smem (8 outputs + up to 8 taps to the right)
 
-__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr) {
-    // K-major SWIZZLE_128B, SBO = one halo row (16 px * 128 B = 2048 B), base offset = 128-byte row phase of the start
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((kHaloPitch * 128) >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)(MR_HALO_BASE_OFFSET ? ((saddr >> 7) & 7) : 0) << 49) | ((uint64_t)2 << 61);
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_bytes) {
+    // K-major swizzled (128- or 64-byte rows), SBO = one halo row (16 px), base offset 0: the swizzle is a function of the
+    // absolute shared-memory address; MR_HALO_BASE_OFFSET=1 restores the row-phase variant for experiments
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((kHaloPitch * row_bytes) >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)(MR_HALO_BASE_OFFSET ? ((saddr >> 7) & 7) : 0) << 49) |
+           ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
 }
 
 __global__ void __launch_bounds__(kTcThreads)
@@ -434,11 +436,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_bytes = (uint32_t)a.n_pad * 128u;
+    const uint32_t row_bytes = (uint32_t)a.row_bytes;
+    const uint32_t b_bytes = (uint32_t)a.n_pad * row_bytes;
     const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
     const int taps = a.kh * a.kw;
-    const uint32_t bres_bytes = (uint32_t)(taps * chunks_per_tap) * b_bytes;       // multiple of 1024 (n_pad % 16 == 0 -> % 2048)
-    const uint32_t a_bytes = (uint32_t)(16 + a.kh - 1) * kHaloPitch * 128u;
+    const uint32_t bres_bytes = (uint32_t)(taps * chunks_per_tap) * b_bytes;       // multiple of 1024 (n_pad % 16 == 0)
+    const uint32_t a_bytes = (uint32_t)(16 + a.kh - 1) * kHaloPitch * row_bytes;   // multiple of 1024 (pitch 16)
     const uint32_t a_base = base + ((bres_bytes + 1023u) & ~1023u);
     const int stages = a.stages;
     const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[4]);
@@ -511,10 +514,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const uint32_t sa = a_base + st * a_bytes;
                     for (int ky = 0; ky < a.kh; ++ky)
                         for (int kx = 0; kx < a.kw; ++kx) {
-                            const uint64_t da = make_desc_halo(sa + (uint32_t)(ky * kHaloPitch + kx) * 128u);
-                            const uint64_t db = make_desc(base + (uint32_t)((ky * a.kw + kx) * chunks_per_tap + cg) * b_bytes);
+                            const uint64_t da = make_desc_halo(sa + (uint32_t)(ky * kHaloPitch + kx) * row_bytes, row_bytes);
+                            const uint32_t sb = base + (uint32_t)((ky * a.kw + kx) * chunks_per_tap + cg) * b_bytes;
+                            const uint64_t db = (uint64_t)((sb & 0x3FFFF) >> 4) | a.desc_hi;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {   // 4 x 32 bytes of K per 128-byte row (8 tf32 / 16 half each)
+                            for (int k = 0; k < 4; ++k) {   // 32 bytes of K per MMA (8 tf32 / 16 half): 4 per 128-byte row, 2 per 64-byte row
+                                if (32u * k >= row_bytes) break;
                                 if (a.f16) umma_f16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
                                 else       umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
                             }
@@ -625,14 +630,17 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     // "halo" variant (one input box per tile, resident weights): stride 1, taps reach at most 8 px to the right, weights fit
     int chunks_all = 0;
     for (int s = 0; s < d.n_src; ++s) chunks_all += (d.src_c[s] + kc - 1) / kc;
-    const size_t bres = (size_t)d.kh * d.kw * chunks_all * n_pad * 128;
+    const size_t bres = (size_t)d.kh * d.kw * chunks_all * n_pad * a.row_bytes;
     // MONOREC_B200_TC_HALO: unset = automatic, 0 = never, 1 / 2 = always when eligible with that many CTAs per SM.
     // Automatic (measured on the stacks' layers): only when weights + two halo stages fit twice per SM, i.e. two CTAs per
     // SM (32->32 3x3 over the single-frame volumes: 631 -> 452 us in TF32, 489 -> 429 us in half); with a single CTA per SM
     // its four epilogue warps become the bottleneck (48->48 3x3: 300 -> 335 us), so those layers keep the tap-refetch kernel.
     static const int halo_env = getenv("MONOREC_B200_TC_HALO") ? atoi(getenv("MONOREC_B200_TC_HALO")) : -1;
     static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : true;
-    const size_t halo_a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * 128;
+    // 64-byte rows inside the halo box (half sources of <= 32 channels packed with 32-channel chunks): not yet measured on the
+    // GPU, therefore opt-in; the Python side packs such layers with 64-channel chunks unless this is set
+    static const bool halo_k32 = getenv("MONOREC_B200_TC_HALO_K32") ? (atoi(getenv("MONOREC_B200_TC_HALO_K32")) != 0) : false;
+    const size_t halo_a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * a.row_bytes;
     const size_t bres_al = (bres + 1023) & ~size_t(1023);
     auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights (228 KB per SM, 1 KB reserved + ~1.1 KB static per CTA)
         const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas;
@@ -640,7 +648,7 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         return st > 4 ? 4 : st;
     };
     int halo_ctas = 0;
-    if (halo_env != 0 && (!f16 || halo_f16) && a.row_bytes == 128 && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
+    if (halo_env != 0 && (!f16 || halo_f16) && (a.row_bytes == 128 || halo_k32) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
         if (halo_env == 1 || halo_env == 2) halo_ctas = halo_fit(halo_env) >= 2 ? halo_env : 0;
         else if (halo_fit(2) >= 2) halo_ctas = 2;
     }
