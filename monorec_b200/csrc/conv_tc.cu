@@ -263,6 +263,85 @@ __device__ __forceinline__ void epilogue_row_quad(uint32_t trow, const TcArgs& a
     }
 }
 
+// out-of-line copy of the generic epilogue for the staged kernel's rare fallback (keeps its hot code small)
+__device__ __noinline__ void epilogue_row_outofline(uint32_t trow, const TcArgs& a, const float* bias_s, float* op, bool live, bool vec_ok) {
+    epilogue_row(trow, a, bias_s, op, live, vec_ok);
+}
+
+// ---- staged epilogue (conv_tc_kernel<1>, opt-in until measured: MONOREC_B200_TC_EPI=1) -----------------------------------------
+// The source-level profile of the default epilogue (profiles/r01_k2_fullres_f16_quad_ncu_details.txt and the source page of
+// the same capture) shows ~900 executed instructions per warp and tile spread over a 12 700-instruction kernel body
+// (23 % of the stall samples are instruction-fetch misses) -- per-element activation switches, predicates and 48 SEL + 16
+// SHFL per quad transpose.  This variant keeps the per-tile decisions out of the element loop (LeakyReLU as max(x, slope*x)
+// with slope = 1 for "no activation", rounding as a template parameter) and transposes through a 2 KB per-warp staging
+// buffer in shared memory instead of shuffles: every thread writes the 64 bytes of its pixel (4 x STS.128, XOR-swizzled,
+// conflict-free), then lane l reads chunk l%4 of pixel l/4 + 8k and stores it, so that one store instruction covers 8
+// pixels x 64 contiguous bytes.  One step = 16 fp32 or 32 half output channels.
+template <bool OUT_F16, bool ROUND>
+__device__ __forceinline__ void epilogue_staged(uint32_t trow, const TcArgs& a, const float* bias_s, uint32_t stg, uint8_t* const (&qptr)[4],
+                                                const bool (&qlive)[4], int lane, float slope) {
+    constexpr int kCols = OUT_F16 ? 32 : 16;        // output channels per 64-byte step
+    constexpr int kChunk = OUT_F16 ? 8 : 4;         // channels per 16-byte chunk
+    const uint32_t wrow = stg + (uint32_t)lane * 64u;
+    const uint32_t wsw = ((uint32_t)lane >> 1) & 3u;
+    const uint32_t c = (uint32_t)lane & 3u;
+    uint32_t raddr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t q = ((uint32_t)lane >> 2) + 8u * k;
+        raddr[k] = stg + q * 64u + ((c ^ ((q >> 1) & 3u)) << 4);
+    }
+    for (int n0 = 0; n0 < a.n_pad; n0 += kCols) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16_nowait(trow + (uint32_t)n0, r0);
+        const bool second = OUT_F16 && (n0 + 16 < a.n_pad);
+        if (second) tmem_ld16_nowait(trow + (uint32_t)(n0 + 16), r1);
+        tmem_ld_wait();
+        uint4 e[4];
+        if (OUT_F16) {
+            __half2* h = reinterpret_cast<__half2*>(e);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float x0 = __uint_as_float(r0[2 * j]) + bias_s[n0 + 2 * j], x1 = __uint_as_float(r0[2 * j + 1]) + bias_s[n0 + 2 * j + 1];
+                h[j] = __floats2half2_rn(fmaxf(x0, slope * x0), fmaxf(x1, slope * x1));
+            }
+            if (second) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float x0 = __uint_as_float(r1[2 * j]) + bias_s[n0 + 16 + 2 * j], x1 = __uint_as_float(r1[2 * j + 1]) + bias_s[n0 + 17 + 2 * j];
+                    h[8 + j] = __floats2half2_rn(fmaxf(x0, slope * x0), fmaxf(x1, slope * x1));
+                }
+            } else {
+                e[2] = make_uint4(0u, 0u, 0u, 0u);
+                e[3] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+            uint32_t* w = reinterpret_cast<uint32_t*>(e);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(r0[j]) + bias_s[n0 + j];
+                x = fmaxf(x, slope * x);
+                w[j] = ROUND ? ((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u) : __float_as_uint(x);
+            }
+        }
+#pragma unroll
+        for (uint32_t cc = 0; cc < 4; ++cc)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow + ((cc ^ wsw) << 4)), "r"(e[cc].x), "r"(e[cc].y),
+                         "r"(e[cc].z), "r"(e[cc].w)
+                         : "memory");
+        __syncwarp();
+        const bool col_ok = n0 + (int)c * kChunk + kChunk <= a.Cout;
+        const size_t boff = ((size_t)n0 * (OUT_F16 ? 2 : 4)) + (size_t)c * 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(raddr[k]) : "memory");
+            if (qlive[k] && col_ok) *reinterpret_cast<uint4*>(qptr[k] + boff) = v;
+        }
+        __syncwarp();
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -270,6 +349,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent: each CTA loops over output tiles (tile = blockIdx.x, += gridDim.x).  The TMA->MMA shared-memory ring keeps
 // flowing across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the
 // main loop of tile i+1.
+template <int EPI>   // 0: register epilogues (default), 1: staged epilogue above
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -368,6 +448,51 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
                 __syncwarp();
             }
+        }
+    } else if constexpr (EPI == 1) {
+        // ===================== epilogue, staged through shared memory (see epilogue_staged) =====================
+        __shared__ __align__(16) uint8_t stage_s[4][2048];
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read (the 4 epilogue warps have distinct ones)
+        const int p = 32 * q + lane;
+        const uint32_t stg = smem_u32(&stage_s[q][0]);
+        const size_t esize = a.out_f16 ? 2 : 4;
+        const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
+        const bool lean_ok = vec_ok && (a.Cout & (a.out_f16 ? 7 : 3)) == 0 && !(a.out_f16 && a.round_out) &&
+                             (a.act == MR_ACT_NONE || a.act == MR_ACT_LEAKY);
+        const float slope = a.act == MR_ACT_LEAKY ? a.act_a : 1.0f;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+            uint8_t* qptr[4];
+            bool qlive[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {       // the 4 pixels this lane stores for: accumulator rows 32q + lane/4 + 8k
+                const int pq = 32 * q + (lane >> 2) + 8 * k;
+                const int qy = tile_y * kTileH + (pq >> 4), qx = tile_x * kTileW + (pq & 15);
+                qlive[k] = (qy < a.Ho) && (qx < a.Wo);
+                const size_t qidx = (((size_t)b * a.dst_H + (qy * a.oy_step + a.oy_off)) * a.dst_W + (qx * a.ox_step + a.ox_off)) *
+                                        a.dst_c + a.dst_coff;
+                qptr[k] = reinterpret_cast<uint8_t*>(a.dst) + qidx * esize;
+            }
+            const int buf = lt & 1;
+            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
+            if (lean_ok) {
+                if (a.out_f16) epilogue_staged<true, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+                else if (a.round_out) epilogue_staged<false, true>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+                else epilogue_staged<false, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+            } else {
+                const int oy = tile_y * kTileH + (p >> 4), ox = tile_x * kTileW + (p & 15);
+                const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+                                        a.dst_c + a.dst_coff;
+                float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
+                epilogue_row_outofline(trow, a, bias_s, op, (oy < a.Ho) && (ox < a.Wo), vec_ok);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> bias/activation -> NHWC =====================
@@ -713,7 +838,9 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     int ctas_per_sm = (int)(512 / cols_needed);
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     if (kForceCtas > 0 && (uint32_t)kForceCtas * cols_needed <= 512) ctas_per_sm = kForceCtas;
-    const size_t budget = (size_t)(200 * 1024) / ctas_per_sm;
+    // experimental staged epilogue (conv_tc_kernel<1>): 8 KB of static shared memory per CTA more
+    static const bool kStagedEpi = getenv("MONOREC_B200_TC_EPI") ? (atoi(getenv("MONOREC_B200_TC_EPI")) == 1) : false;
+    const size_t budget = (size_t)(200 * 1024) / ctas_per_sm - (kStagedEpi ? 8 * 1024 : 0);
     int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -736,10 +863,15 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         return MR_OK;
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024;
-    MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     int grid = sms * ctas_per_sm;
     if (grid > a.total_tiles) grid = a.total_tiles;
-    conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+    if (kStagedEpi) {
+        MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(212 * 1024)));
+        conv_tc_kernel<1><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+    } else {
+        MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+        conv_tc_kernel<0><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+    }
     MR_LAUNCH_CHECK("conv_tc_kernel");
     return MR_OK;
 }

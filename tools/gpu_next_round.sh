@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of the next round: measure what round 1 could only prepare (no GPU minutes were left).
+#   1. tools/ubench_tc.cu: tcgen05.mma issue cost vs shape / chains / CTAs, TMA box rates for the boxes the conv kernels use
+#   2. parity + timing of the opt-in conv variants: staged epilogue (MONOREC_B200_TC_EPI=1), 64-byte rows inside the halo box
+#      (MONOREC_B200_TC_HALO_K32=1), both together
+mkdir -p gpurun_out
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ubench_tc tools/ubench_tc.cu && timeout 300 /tmp/ubench_tc > gpurun_out/ubench_tc.txt 2>&1; tail -5 gpurun_out/ubench_tc.txt
+run() {  # name, env assignments...
+  local name=$1; shift
+  echo "== $name"
+  env "$@" timeout 600 python -m pytest tests/test_convnet_gpu.py -x -q 2>&1 | tail -1
+  for m in f16 tf32; do echo -n "$m: "; env "$@" MONOREC_B200_CONV=$m timeout 200 python tools/profile_model.py 8 4 10 2>&1 | tail -1; done
+  env "$@" MONOREC_B200_CONV=f16 timeout 200 python tools/bench_conv_layers.py 2>&1 | tail -7
+}
+run "default" MONOREC_B200_NOOP=1
+run "staged epilogue" MONOREC_B200_TC_EPI=1
+run "staged epilogue, no halo" MONOREC_B200_TC_EPI=1 MONOREC_B200_TC_HALO=0
+run "halo with 64-byte rows" MONOREC_B200_TC_HALO_K32=1
