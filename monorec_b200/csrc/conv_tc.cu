@@ -551,6 +551,7 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_
            ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
 }
 
+template <int ROWB>   // bytes per shared-memory row: 128 (default) or 64 (opt-in, half sources of <= 32 channels)
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -561,7 +562,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t row_bytes = (uint32_t)a.row_bytes;
+    constexpr uint32_t row_bytes = (uint32_t)ROWB;
     const uint32_t b_bytes = (uint32_t)a.n_pad * row_bytes;
     const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
     const int taps = a.kh * a.kw;
@@ -641,10 +642,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         for (int kx = 0; kx < a.kw; ++kx) {
                             const uint64_t da = make_desc_halo(sa + (uint32_t)(ky * kHaloPitch + kx) * row_bytes, row_bytes);
                             const uint32_t sb = base + (uint32_t)((ky * a.kw + kx) * chunks_per_tap + cg) * b_bytes;
-                            const uint64_t db = (uint64_t)((sb & 0x3FFFF) >> 4) | a.desc_hi;
+                            const uint64_t db = (uint64_t)((sb & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) |
+                                                ((uint64_t)1 << 46) | ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {   // 32 bytes of K per MMA (8 tf32 / 16 half): 4 per 128-byte row, 2 per 64-byte row
-                                if (32u * k >= row_bytes) break;
+                            for (int k = 0; k < ROWB / 32; ++k) {   // 32 bytes of K per MMA (8 tf32 / 16 half): 4 per 128-byte row, 2 per 64-byte row
                                 if (a.f16) umma_f16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
                                 else       umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
                             }
@@ -855,10 +856,15 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     if (halo) {
         a.stages = halo_stages;
         const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
-        MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
         int grid = sms * halo_ctas;
         if (grid > a.total_tiles) grid = a.total_tiles;
-        conv_tc_halo_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+        if (a.row_bytes == 128) {
+            MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+            conv_tc_halo_kernel<128><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+        } else {
+            MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+            conv_tc_halo_kernel<64><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+        }
         MR_LAUNCH_CHECK("conv_tc_halo_kernel");
         return MR_OK;
     }

@@ -82,39 +82,48 @@ extern "C" int mr_cost_volume_host(const float* h_keyframe, const float* h_frame
     StreamRing ring;
     int rc = ring.init();
     if (rc != MR_OK) return rc;
-    cudaStream_t s0 = ring.st[0];
-    MR_CUDA(cudaMemcpyAsync(d_kpose, h_keyframe_pose, (size_t)B * 64, cudaMemcpyHostToDevice, s0));
-    MR_CUDA(cudaMemcpyAsync(d_kK, h_keyframe_K, (size_t)B * 64, cudaMemcpyHostToDevice, s0));
-    MR_CUDA(cudaMemcpyAsync(d_poses, h_poses, (size_t)F * B * 64, cudaMemcpyHostToDevice, s0));
-    MR_CUDA(cudaMemcpyAsync(d_intr, h_intrinsics, (size_t)F * B * 64, cudaMemcpyHostToDevice, s0));
-    const float* pp[MR_MAX_FRAMES];
-    const float* ip[MR_MAX_FRAMES];
-    const float* fp[MR_MAX_FRAMES];
-    for (int f = 0; f < F; ++f) {
-        pp[f] = d_poses + (size_t)f * B * 16;
-        ip[f] = d_intr + (size_t)f * B * 16;
-        fp[f] = d_frames + (size_t)f * B * img1;
-    }
-    rc = mr_projection_tables(d_kpose, d_kK, pp, ip, B, F, H, W, d_proj, d_depths, D, inv_depth_lo, inv_depth_hi, s0);
-    if (rc != MR_OK) return rc;
-    MR_CUDA(cudaEventRecord(ring.ready, s0));
-    for (int b = 0; b < B; ++b) {
-        cudaStream_t s = ring.st[b % kStreams];
-        MR_CUDA(cudaMemcpyAsync(d_key + b * img1, h_keyframe + b * img1, img1 * 4, cudaMemcpyHostToDevice, s));
+    // everything below only enqueues work; whatever happens, the internal streams are drained before returning so that no
+    // copy into the caller's buffers is still in flight (and the first error, if any, is the one reported)
+    auto enqueue = [&]() -> int {
+        cudaStream_t s0 = ring.st[0];
+        MR_CUDA(cudaMemcpyAsync(d_kpose, h_keyframe_pose, (size_t)B * 64, cudaMemcpyHostToDevice, s0));
+        MR_CUDA(cudaMemcpyAsync(d_kK, h_keyframe_K, (size_t)B * 64, cudaMemcpyHostToDevice, s0));
+        MR_CUDA(cudaMemcpyAsync(d_poses, h_poses, (size_t)F * B * 64, cudaMemcpyHostToDevice, s0));
+        MR_CUDA(cudaMemcpyAsync(d_intr, h_intrinsics, (size_t)F * B * 64, cudaMemcpyHostToDevice, s0));
+        const float* pp[MR_MAX_FRAMES];
+        const float* ip[MR_MAX_FRAMES];
+        const float* fp[MR_MAX_FRAMES];
         for (int f = 0; f < F; ++f) {
-            size_t o = ((size_t)f * B + b) * img1;
-            MR_CUDA(cudaMemcpyAsync(d_frames + o, h_frames + o, img1 * 4, cudaMemcpyHostToDevice, s));
+            pp[f] = d_poses + (size_t)f * B * 16;
+            ip[f] = d_intr + (size_t)f * B * 16;
+            fp[f] = d_frames + (size_t)f * B * img1;
         }
-        MR_CUDA(cudaStreamWaitEvent(s, ring.ready, 0));
-        rc = mr::launch_cost_volume(d_key, fp, d_proj, d_depths, d_cv, d_sfcv, B, F, D, H, W, alpha, nullptr, b, 1, ws + p.packed,
-                                    (long long)F * B * H * W * 16, s);
+        rc = mr_projection_tables(d_kpose, d_kK, pp, ip, B, F, H, W, d_proj, d_depths, D, inv_depth_lo, inv_depth_hi, s0);
         if (rc != MR_OK) return rc;
-        MR_CUDA(cudaMemcpyAsync(h_out_cv + b * vol1, d_cv + b * vol1, vol1 * 4, cudaMemcpyDeviceToHost, s));
-        for (int f = 0; f < F; ++f) {
-            size_t o = ((size_t)f * B + b) * vol1;
-            MR_CUDA(cudaMemcpyAsync(h_out_sfcv + o, d_sfcv + o, vol1 * 4, cudaMemcpyDeviceToHost, s));
+        MR_CUDA(cudaEventRecord(ring.ready, s0));
+        for (int b = 0; b < B; ++b) {
+            cudaStream_t s = ring.st[b % kStreams];
+            MR_CUDA(cudaMemcpyAsync(d_key + b * img1, h_keyframe + b * img1, img1 * 4, cudaMemcpyHostToDevice, s));
+            for (int f = 0; f < F; ++f) {
+                size_t o = ((size_t)f * B + b) * img1;
+                MR_CUDA(cudaMemcpyAsync(d_frames + o, h_frames + o, img1 * 4, cudaMemcpyHostToDevice, s));
+            }
+            MR_CUDA(cudaStreamWaitEvent(s, ring.ready, 0));
+            rc = mr::launch_cost_volume(d_key, fp, d_proj, d_depths, d_cv, d_sfcv, B, F, D, H, W, alpha, nullptr, b, 1, ws + p.packed,
+                                        (long long)F * B * H * W * 16, s);
+            if (rc != MR_OK) return rc;
+            MR_CUDA(cudaMemcpyAsync(h_out_cv + b * vol1, d_cv + b * vol1, vol1 * 4, cudaMemcpyDeviceToHost, s));
+            for (int f = 0; f < F; ++f) {
+                size_t o = ((size_t)f * B + b) * vol1;
+                MR_CUDA(cudaMemcpyAsync(h_out_sfcv + o, d_sfcv + o, vol1 * 4, cudaMemcpyDeviceToHost, s));
+            }
         }
+        return MR_OK;
+    };
+    rc = enqueue();
+    for (int i = 0; i < ring.n; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(ring.st[i]);
+        if (rc == MR_OK && e != cudaSuccess) rc = mr::check_cuda(e, "mr_cost_volume_host: cudaStreamSynchronize");
     }
-    for (int i = 0; i < kStreams; ++i) MR_CUDA(cudaStreamSynchronize(ring.st[i]));
-    return MR_OK;
+    return rc;
 }
