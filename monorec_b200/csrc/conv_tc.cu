@@ -342,6 +342,38 @@ __device__ __forceinline__ void epilogue_staged(uint32_t trow, const TcArgs& a, 
     }
 }
 
+// One tile of the staged epilogue for a warp (TMEM lane quadrant q): output pointers / liveness of the 4 pixels each lane
+// stores for, then the 64-byte steps; tiles are kTW x kTH pixels with accumulator row p = y * kTW + x.  Layers the staged
+// path cannot take (unaligned channel slices, the rare activations) go through the generic out-of-line epilogue.
+template <int kTW, int kTH>
+__device__ __forceinline__ void staged_tile(const TcArgs& a, const float* bias_s, uint32_t stg, int q, int lane, int b, int tile_y,
+                                            int tile_x, uint32_t trow, bool lean_ok, bool vec_ok, float slope) {
+    if (lean_ok) {
+        const size_t esize = a.out_f16 ? 2 : 4;
+        uint8_t* qptr[4];
+        bool qlive[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {       // accumulator rows 32q + lane/4 + 8k
+            const int pq = 32 * q + (lane >> 2) + 8 * k;
+            const int qy = tile_y * kTH + pq / kTW, qx = tile_x * kTW + pq % kTW;
+            qlive[k] = (qy < a.Ho) && (qx < a.Wo);
+            const size_t qidx = (((size_t)b * a.dst_H + (qy * a.oy_step + a.oy_off)) * a.dst_W + (qx * a.ox_step + a.ox_off)) *
+                                    a.dst_c + a.dst_coff;
+            qptr[k] = reinterpret_cast<uint8_t*>(a.dst) + qidx * esize;
+        }
+        if (a.out_f16) epilogue_staged<true, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+        else if (a.round_out) epilogue_staged<false, true>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+        else epilogue_staged<false, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+    } else {
+        const int p = 32 * q + lane;
+        const int oy = tile_y * kTH + p / kTW, ox = tile_x * kTW + p % kTW;
+        const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+                                a.dst_c + a.dst_coff;
+        float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
+        epilogue_row_outofline(trow, a, bias_s, op, (oy < a.Ho) && (ox < a.Wo), vec_ok);
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -453,9 +485,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ===================== epilogue, staged through shared memory (see epilogue_staged) =====================
         __shared__ __align__(16) uint8_t stage_s[4][2048];
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read (the 4 epilogue warps have distinct ones)
-        const int p = 32 * q + lane;
         const uint32_t stg = smem_u32(&stage_s[q][0]);
-        const size_t esize = a.out_f16 ? 2 : 4;
         const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
         const bool lean_ok = vec_ok && (a.Cout & (a.out_f16 ? 7 : 3)) == 0 && !(a.out_f16 && a.round_out) &&
                              (a.act == MR_ACT_NONE || a.act == MR_ACT_LEAKY);
@@ -464,32 +494,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
             const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
-            uint8_t* qptr[4];
-            bool qlive[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {       // the 4 pixels this lane stores for: accumulator rows 32q + lane/4 + 8k
-                const int pq = 32 * q + (lane >> 2) + 8 * k;
-                const int qy = tile_y * kTileH + (pq >> 4), qx = tile_x * kTileW + (pq & 15);
-                qlive[k] = (qy < a.Ho) && (qx < a.Wo);
-                const size_t qidx = (((size_t)b * a.dst_H + (qy * a.oy_step + a.oy_off)) * a.dst_W + (qx * a.ox_step + a.ox_off)) *
-                                        a.dst_c + a.dst_coff;
-                qptr[k] = reinterpret_cast<uint8_t*>(a.dst) + qidx * esize;
-            }
             const int buf = lt & 1;
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            if (lean_ok) {
-                if (a.out_f16) epilogue_staged<true, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
-                else if (a.round_out) epilogue_staged<false, true>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
-                else epilogue_staged<false, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
-            } else {
-                const int oy = tile_y * kTileH + (p >> 4), ox = tile_x * kTileW + (p & 15);
-                const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
-                                        a.dst_c + a.dst_coff;
-                float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
-                epilogue_row_outofline(trow, a, bias_s, op, (oy < a.Ho) && (ox < a.Wo), vec_ok);
-            }
+            staged_tile<kTileW, kTileH>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -551,8 +560,8 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_
            ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
 }
 
-template <int ROWB>   // bytes per shared-memory row: 128 (default) or 64 (opt-in, half sources of <= 32 channels)
-__global__ void __launch_bounds__(kTcThreads)
+template <int ROWB, int EPI>   // ROWB: bytes per shared-memory row, 128 (default) or 64 (opt-in, half sources of <= 32
+__global__ void __launch_bounds__(kTcThreads)   // channels); EPI: 0 register epilogues (default), 1 staged epilogue (opt-in)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -655,6 +664,28 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
                 __syncwarp();
             }
+        }
+    } else if constexpr (EPI == 1) {
+        // ===================== epilogue, staged through shared memory (tile = 16 rows x 8 columns) =====================
+        __shared__ __align__(16) uint8_t stage_s[4][2048];
+        const int q = warp & 3;
+        const uint32_t stg = smem_u32(&stage_s[q][0]);
+        const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
+        const bool lean_ok = vec_ok && (a.Cout & (a.out_f16 ? 7 : 3)) == 0 && !(a.out_f16 && a.round_out) &&
+                             (a.act == MR_ACT_NONE || a.act == MR_ACT_LEAKY);
+        const float slope = a.act == MR_ACT_LEAKY ? a.act_a : 1.0f;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+            const int buf = lt & 1;
+            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
+            staged_tile<8, 16>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
     } else {
         // ===================== epilogue (tile = 16 rows x 8 columns) =====================
@@ -762,6 +793,8 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     // SM (32->32 3x3 over the single-frame volumes: 631 -> 452 us in TF32, 489 -> 429 us in half); with a single CTA per SM
     // its four epilogue warps become the bottleneck (48->48 3x3: 300 -> 335 us), so those layers keep the tap-refetch kernel.
     static const int halo_env = getenv("MONOREC_B200_TC_HALO") ? atoi(getenv("MONOREC_B200_TC_HALO")) : -1;
+    // experimental staged epilogue (conv_tc_kernel<1>, conv_tc_halo_kernel<.,1>): 8 KB of static shared memory per CTA more
+    static const bool kStagedEpi = getenv("MONOREC_B200_TC_EPI") ? (atoi(getenv("MONOREC_B200_TC_EPI")) == 1) : false;
     static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : true;
     // 64-byte rows inside the halo box (half sources of <= 32 channels packed with 32-channel chunks): not yet measured on the
     // GPU, therefore opt-in; the Python side packs such layers with 64-channel chunks unless this is set
@@ -769,7 +802,7 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     const size_t halo_a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * a.row_bytes;
     const size_t bres_al = (bres + 1023) & ~size_t(1023);
     auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights (228 KB per SM, 1 KB reserved + ~1.1 KB static per CTA)
-        const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas;
+        const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas - (kStagedEpi ? 8 * 1024 : 0);
         int st = bres_al + 2048 < budget ? (int)((budget - 2048 - bres_al) / halo_a_bytes) : 0;
         return st > 4 ? 4 : st;
     };
@@ -839,8 +872,6 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     int ctas_per_sm = (int)(512 / cols_needed);
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     if (kForceCtas > 0 && (uint32_t)kForceCtas * cols_needed <= 512) ctas_per_sm = kForceCtas;
-    // experimental staged epilogue (conv_tc_kernel<1>): 8 KB of static shared memory per CTA more
-    static const bool kStagedEpi = getenv("MONOREC_B200_TC_EPI") ? (atoi(getenv("MONOREC_B200_TC_EPI")) == 1) : false;
     const size_t budget = (size_t)(200 * 1024) / ctas_per_sm - (kStagedEpi ? 8 * 1024 : 0);
     int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
@@ -858,13 +889,15 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
         int grid = sms * halo_ctas;
         if (grid > a.total_tiles) grid = a.total_tiles;
-        if (a.row_bytes == 128) {
-            MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-            conv_tc_halo_kernel<128><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
-        } else {
-            MR_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-            conv_tc_halo_kernel<64><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
-        }
+        auto launch_halo = [&](auto kernel) -> int {
+            MR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(212 * 1024)));
+            kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+            return MR_OK;
+        };
+        int lrc;
+        if (a.row_bytes == 128) lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<128, 1>) : launch_halo(conv_tc_halo_kernel<128, 0>);
+        else lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<64, 1>) : launch_halo(conv_tc_halo_kernel<64, 0>);
+        if (lrc != MR_OK) return lrc;
         MR_LAUNCH_CHECK("conv_tc_halo_kernel");
         return MR_OK;
     }

@@ -30,8 +30,7 @@ for line in out.splitlines():
     line = re.sub(r"/\* 0x[0-9a-f]+ \*/", "", line)            # encodings
     line = re.sub(r"0x[0-9a-f]{6,}", "ADDR", line)             # absolute branch targets
     line = re.sub(r"\s+", " ", line).strip()
-    if line and not line.startswith(".") and "Fatbin" not in line and "arch =" not in line and "code version" not in line \
-            and "host =" not in line and "compile_size" not in line and "producer" not in line and line != "=" * len(line):
+    if line.endswith(";"):                                     # instructions only (headers mention the mangled name)
         body.append(line)
 flush()
 for k in sorted(digests):
