@@ -92,3 +92,25 @@ def test_trunk_batchnorm_folding_matches_unfolded_eval():
     with torch.enable_grad():
         ref2 = enc(x)[0].detach()
     assert float((out2 - ref2).abs().max()) < 1e-4 and float((out2 - out[0]).abs().max()) > 0.5
+
+
+def test_tc_weight_packing_chunk_widths():
+    """Packed tensor-core weights: [taps][n_pad][k_pad], every source padded to whole K chunks; half sources of <= 32
+    channels use 32-channel chunks (64-byte swizzle rows) except on stride-1 layers, which the halo kernel takes with
+    64-channel chunks (the library derives the chunk width from k_pad: include/monorec_b200.h)."""
+    from monorec_b200 import conv as C
+    w = torch.randn(24, 32, 3, 3)
+    wt, n_pad, k_pad = C.pack_tc_weight(w, (32,), half=False)
+    assert wt.dtype == torch.float32 and wt.shape == (9, 32, 32) and (n_pad, k_pad) == (32, 32)
+    assert torch.equal(wt[4, :24, :], C._round_tf32(w[:, :, 1, 1])) and float(wt[:, 24:].abs().max()) == 0.0
+    wt, n_pad, k_pad = C.pack_tc_weight(w, (32,), half=True, allow_k32=True)
+    assert wt.dtype == torch.float16 and k_pad == (32 if C.K32 else 64) and wt.shape == (9, 32, k_pad)
+    wt, n_pad, k_pad = C.pack_tc_weight(w, (32,), half=True, allow_k32=False)
+    assert k_pad == 64 and float(wt[:, :, 32:].abs().max()) == 0.0
+    w2 = torch.randn(48, 96, 3, 3)
+    wt, n_pad, k_pad = C.pack_tc_weight(w2, (32, 64), half=True)          # a 64-channel source keeps 64-channel chunks
+    assert (n_pad, k_pad) == (48, 128) and torch.equal(wt[0, :, 64:128], w2[:, 32:, 0, 0].half())
+    assert float(wt[:, :, 32:64].abs().max()) == 0.0
+    s1 = C.PackedConv(w, None, (32,), stride=(1, 1))
+    s2 = C.PackedConv(w, None, (32,), stride=(2, 1))
+    assert s1.wtc(True)[2] == (64 if (C.HALO_F16 and not C.HALO_K32) else 32) and s2.wtc(True)[2] == (32 if C.K32 else 64)
