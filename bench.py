@@ -343,6 +343,35 @@ def main():
                              "batch_per_gpu": B, "conv_arithmetic": mode, "gathered_result_shape": list(res.shape),
                              "what": "MonoRecModel.forward (CUDA-graph replay) + NCCL all-gather of result; "
                                      "inputs resident, random-init weights"}
+            # the same forward from pinned HOST tensors to a HOST result (what example/test_monorec.py:45-53 does with
+            # to(batch, device) ... .cpu()): H2D of the dict + graph replay + D2H of `result` inside the timed region.
+            # Informational and guarded: a failure here must never cost the JSON line.
+            try:
+                hsets = []
+                for i in range(2):
+                    hd = make_inputs(B, F, H, W, seed=900 + 10 * rank + i)
+                    hsets.append({k: ([t.contiguous().pin_memory() for t in v] if isinstance(v, (list, tuple)) else
+                                      (v.contiguous().pin_memory() if torch.is_tensor(v) else v)) for k, v in hd.items()})
+                h_res = torch.empty(B, 1, H, W).pin_memory()
+
+                def host_step(i):
+                    out = gm(hsets[i % 2])["result"]
+                    h_res.copy_(out, non_blocking=True)
+                    torch.cuda.synchronize()
+                for i in range(2):
+                    host_step(i)
+                t0 = time.perf_counter()          # no collective in this guarded block: rank 0's own clock, x world
+                for i in range(10):
+                    host_step(i)
+                dt = torch.tensor([time.perf_counter() - t0])
+                if rank == 0:
+                    h2d = sum(t.numel() * t.element_size() for v in hsets[0].values()
+                              for t in (v if isinstance(v, (list, tuple)) else [v]) if torch.is_tensor(t))
+                    line[key]["host_to_host"] = {"value": world * B * 10 / float(dt.item()), "unit": "keyframes/s",
+                                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_res.numel() * 4}
+            except Exception as exc:   # noqa: BLE001
+                if rank == 0 and line is not None and key in line:
+                    line[key]["host_to_host_error"] = f"{type(exc).__name__}: {exc}"[:200]
             del gm
         C.set_mode(default_mode)
         del model
