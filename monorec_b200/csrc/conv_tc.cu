@@ -560,12 +560,16 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_
            ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
 }
 
-template <int ROWB, int EPI>   // ROWB: bytes per shared-memory row, 128 (default) or 64 (opt-in, half sources of <= 32
-__global__ void __launch_bounds__(kTcThreads)   // channels); EPI: 0 register epilogues (default), 1 staged epilogue (opt-in)
+// ROWB: bytes per shared-memory row, 128 (default) or 64 (opt-in, half sources of <= 32 channels); EPI: 0 register epilogues
+// (default), 1 staged epilogue (opt-in); GROUPS: groups of 4 epilogue warps (1 default; 2 = 8 epilogue warps over 4 TMEM
+// accumulators, opt-in, for the layers that only fit one CTA per SM)
+template <int ROWB, int EPI, int GROUPS>
+__global__ void __launch_bounds__(kTcThreads + 128 * (GROUPS - 1))
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * 4 + 4 + 1];   // afull[4], aempty[4], tmem_full[2], tmem_empty[2], bfull
+    constexpr int kBufs = 2 * GROUPS;                            // TMEM accumulators: two per epilogue group
+    __shared__ __align__(8) uint64_t bars[2 * 4 + 2 * kBufs + 1];   // afull[4], aempty[4], tmem_full[kBufs], tmem_empty[kBufs], bfull
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[256];
 
@@ -580,11 +584,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t a_base = base + ((bres_bytes + 1023u) & ~1023u);
     const int stages = a.stages;
     const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[4]);
-    const uint32_t tfull0 = smem_u32(&bars[8]), tempty0 = smem_u32(&bars[10]), bfull = smem_u32(&bars[12]);
+    const uint32_t tfull0 = smem_u32(&bars[8]), tempty0 = smem_u32(&bars[8 + kBufs]), bfull = smem_u32(&bars[8 + 2 * kBufs]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+        for (int s = 0; s < kBufs; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -636,8 +640,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         mbar_wait(bfull, 0);
         int it = 0, lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
-            const int buf = lt & 1;
-            mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);
+            const int buf = lt & (kBufs - 1);
+            mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> (GROUPS == 1 ? 1 : 2)) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_d + (uint32_t)(buf * a.n_pad);
             for (int cg = 0; cg < chunks_per_tap; ++cg, ++it) {
@@ -667,19 +671,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
     } else if constexpr (EPI == 1) {
         // ===================== epilogue, staged through shared memory (tile = 16 rows x 8 columns) =====================
-        __shared__ __align__(16) uint8_t stage_s[4][2048];
-        const int q = warp & 3;
-        const uint32_t stg = smem_u32(&stage_s[q][0]);
+        static_assert(GROUPS == 1 || GROUPS == 2, "one or two groups of four epilogue warps");
+        __shared__ __align__(16) uint8_t stage_s[4 * GROUPS][2048];
+        const int q = warp & 3;                 // TMEM lane quadrant
+        const int g = (warp - 2) >> 2;          // epilogue group: takes the tiles with lt % GROUPS == g
+        const uint32_t stg = smem_u32(&stage_s[warp - 2][0]);
         const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
         const bool lean_ok = vec_ok && (a.Cout & (a.out_f16 ? 7 : 3)) == 0 && !(a.out_f16 && a.round_out) &&
                              (a.act == MR_ACT_NONE || a.act == MR_ACT_LEAKY);
         const float slope = a.act == MR_ACT_LEAKY ? a.act_a : 1.0f;
         int lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
+            if (GROUPS > 1 && (lt & (GROUPS - 1)) != g) continue;
             const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
             const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
-            const int buf = lt & 1;
-            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
+            const int buf = lt & (kBufs - 1);
+            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> (GROUPS == 1 ? 1 : 2)) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
             staged_tile<8, 16>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope);
@@ -702,8 +709,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
                                     a.dst_c + a.dst_coff;
             float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
-            const int buf = lt & 1;
-            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
+            const int buf = lt & (kBufs - 1);
+            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> (GROUPS == 1 ? 1 : 2)) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
             if (quad_ok) epilogue_row_quad(trow, a, bias_s, op, oy < a.Ho, ox, lane);
@@ -806,13 +813,24 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         int st = bres_al + 2048 < budget ? (int)((budget - 2048 - bres_al) / halo_a_bytes) : 0;
         return st > 4 ? 4 : st;
     };
-    int halo_ctas = 0;
+    // 8 epilogue warps + 4 accumulators in a single CTA per SM for the layers that do not fit twice (needs the staged epilogue)
+    static const bool halo_epi8 = getenv("MONOREC_B200_TC_HALO_EPI8") ? (atoi(getenv("MONOREC_B200_TC_HALO_EPI8")) != 0) : false;
+    int halo_ctas = 0, halo_groups = 1;
     if (halo_env != 0 && (!f16 || halo_f16) && (a.row_bytes == 128 || halo_k32) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
         if (halo_env == 1 || halo_env == 2) halo_ctas = halo_fit(halo_env) >= 2 ? halo_env : 0;
         else if (halo_fit(2) >= 2) halo_ctas = 2;
+        else if (halo_epi8 && kStagedEpi && 4 * n_pad <= 512 && d.kh * d.kw >= 3) {
+            // one CTA per SM: weights + >= 2 input stages + 16 KB of staging
+            const size_t budget1 = (size_t)200 * 1024;
+            if (bres_al + 2048 + 2 * halo_a_bytes <= budget1) { halo_ctas = 1; halo_groups = 2; }
+        }
     }
     const bool halo = halo_ctas > 0;
-    const int halo_stages = halo ? halo_fit(halo_ctas) : 0;
+    int halo_stages = halo ? halo_fit(halo_ctas) : 0;
+    if (halo_groups == 2) {   // halo_fit(1) reserves 8 KB of staging; the 8-warp variant needs 16
+        halo_stages = (int)(((size_t)200 * 1024 - 2048 - bres_al) / halo_a_bytes);
+        if (halo_stages > 4) halo_stages = 4;
+    }
     CUtensorMap tmA[MR_CONV_MAX_SRC];
     for (int s = 0; s < d.n_src; ++s) {
         const int C = d.src_c[s];
@@ -889,14 +907,23 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
         const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
         int grid = sms * halo_ctas;
         if (grid > a.total_tiles) grid = a.total_tiles;
-        auto launch_halo = [&](auto kernel) -> int {
+        auto launch_halo = [&](auto kernel, int threads) -> int {
             MR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(212 * 1024)));
-            kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+            kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
             return MR_OK;
         };
         int lrc;
-        if (a.row_bytes == 128) lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<128, 1>) : launch_halo(conv_tc_halo_kernel<128, 0>);
-        else lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<64, 1>) : launch_halo(conv_tc_halo_kernel<64, 0>);
+        if (halo_groups == 2) {          // 8 epilogue warps, 4 accumulators (opt-in, staged epilogue only)
+            uint32_t cols4 = 32;
+            while (cols4 < (uint32_t)(4 * n_pad)) cols4 <<= 1;
+            a.tmem_cols = cols4;
+            lrc = a.row_bytes == 128 ? launch_halo(conv_tc_halo_kernel<128, 1, 2>, kTcThreads + 128)
+                                     : launch_halo(conv_tc_halo_kernel<64, 1, 2>, kTcThreads + 128);
+        } else if (a.row_bytes == 128) {
+            lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<128, 1, 1>, kTcThreads) : launch_halo(conv_tc_halo_kernel<128, 0, 1>, kTcThreads);
+        } else {
+            lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<64, 1, 1>, kTcThreads) : launch_halo(conv_tc_halo_kernel<64, 0, 1>, kTcThreads);
+        }
         if (lrc != MR_OK) return lrc;
         MR_LAUNCH_CHECK("conv_tc_halo_kernel");
         return MR_OK;

@@ -2,7 +2,8 @@
 # First GPU call of the next round: measure what round 1 could only prepare (no GPU minutes were left).
 #   1. tools/ubench_tc.cu: tcgen05.mma issue cost vs shape / chains / CTAs, TMA box rates for the boxes the conv kernels use
 #   2. parity + timing of the opt-in conv variants: staged epilogue (MONOREC_B200_TC_EPI=1), 64-byte rows inside the halo box
-#      (MONOREC_B200_TC_HALO_K32=1), both together
+#      (MONOREC_B200_TC_HALO_K32=1), 8 epilogue warps over 4 accumulators in the single-CTA halo kernel
+#      (MONOREC_B200_TC_HALO_EPI8=1), and their combinations
 mkdir -p gpurun_out
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ubench_tc tools/ubench_tc.cu && timeout 300 /tmp/ubench_tc > gpurun_out/ubench_tc.txt 2>&1; tail -5 gpurun_out/ubench_tc.txt
 run() {  # name, env assignments...
@@ -16,3 +17,5 @@ run "default" MONOREC_B200_NOOP=1
 run "staged epilogue" MONOREC_B200_TC_EPI=1
 run "staged epilogue, no halo" MONOREC_B200_TC_EPI=1 MONOREC_B200_TC_HALO=0
 run "halo with 64-byte rows" MONOREC_B200_TC_HALO_K32=1
+run "staged epilogue + 64-byte halo rows" MONOREC_B200_TC_EPI=1 MONOREC_B200_TC_HALO_K32=1
+run "staged epilogue + 64-byte halo rows + 8-warp halo epilogue" MONOREC_B200_TC_EPI=1 MONOREC_B200_TC_HALO_K32=1 MONOREC_B200_TC_HALO_EPI8=1
