@@ -146,7 +146,8 @@ int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
  * 32 channels (64-byte swizzle rows); the MMA is kind::f16; dst_dtype selects half or float output.
  * Stride-1 layers whose packed weights fit in shared memory twice per SM run on the "halo" variant of the kernel (same
  * results).  Tuning switches (environment, read once): MONOREC_B200_TC_HALO=0|1|2, MONOREC_B200_TC_HALO_F16=0|1,
- * MONOREC_B200_TC_QUAD=0|1, MONOREC_B200_TC_CTAS=n. */
+ * MONOREC_B200_TC_QUAD=0|1, MONOREC_B200_TC_CTAS=n; experimental, off by default: MONOREC_B200_TC_EPI=1 (staged epilogue),
+ * MONOREC_B200_TC_HALO_K32=1 (64-byte rows in the halo kernel), MONOREC_B200_TC_HALO_EPI8=1 (8 epilogue warps). */
 int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream);
 /* sizeof(mr_conv_desc) as compiled into the library (bindings check their mirror of the struct against it). */
 int mr_sizeof_conv_desc(void);
