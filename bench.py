@@ -374,6 +374,30 @@ def main():
                 if rank == 0 and line is not None and key in line:
                     line[key]["host_to_host_error"] = f"{type(exc).__name__}: {exc}"[:200]
             del gm
+        # BASELINE config 3 proper: full model, batch 16, half arithmetic, one GPU (guarded, single-GPU runs only)
+        if world == 1:
+            try:
+                C.set_mode("f16")
+                B16 = 16
+                sets16 = [to_device(make_inputs(B16, F, H, W, seed=500 + i), dev) for i in range(2)]
+                gm = GraphedMonoRec(model, sets16[0])
+                for i in range(3):
+                    gm(sets16[i % 2])
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for i in range(10):
+                    res = gm(sets16[i % 2])["result"]
+                f1.record()
+                torch.cuda.synchronize()
+                fms = f0.elapsed_time(f1) / 10
+                line["full_model_f16_b16"] = {"value": B16 / (fms * 1e-3), "unit": "keyframes/s", "ms_per_forward": fms,
+                                              "batch_per_gpu": B16, "conv_arithmetic": "f16", "result_shape": list(res.shape),
+                                              "what": "BASELINE config 3: MonoRecModel.forward (CUDA-graph replay), batch 16, "
+                                                      "inputs resident (2 rotating sets, 252 MB), random-init weights"}
+                del gm, sets16
+            except Exception as exc:   # noqa: BLE001
+                line["full_model_f16_b16_error"] = f"{type(exc).__name__}: {exc}"[:200]
         C.set_mode(default_mode)
         del model
 
