@@ -50,6 +50,7 @@ struct TcArgs {
     int quad;                      // 1: quad-transposed epilogue stores (64 contiguous bytes per pixel per store instruction)
     int row_bytes;                 // bytes of one K chunk row in shared memory = swizzle span: 128, or 64 (half sources, 32-channel chunks)
     uint64_t desc_hi;              // smem descriptor without the start address (LBO, SBO = 8 rows, version, swizzle mode)
+    const void* residual;          // staged epilogue only: tensor laid out like dst, added before the activation (or null)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -342,6 +343,71 @@ __device__ __forceinline__ void epilogue_staged(uint32_t trow, const TcArgs& a, 
     }
 }
 
+// Residual variant of the staged epilogue (ResNet basic blocks): out = act(acc + bias + residual), residual laid out and
+// typed like the destination.  The pre-activation sums are staged in fp32 (16 channels = 64 bytes per pixel and step); the
+// lane that stores chunk c of pixel q also loads the matching residual chunk, so both accesses are coalesced.
+template <bool OUT_F16>
+__device__ __forceinline__ void epilogue_staged_res(uint32_t trow, const TcArgs& a, const float* bias_s, uint32_t stg, uint8_t* const (&qptr)[4],
+                                                    const bool (&qlive)[4], int lane, float slope) {
+    const uint32_t wrow = stg + (uint32_t)lane * 64u;
+    const uint32_t wsw = ((uint32_t)lane >> 1) & 3u;
+    const uint32_t c = (uint32_t)lane & 3u;
+    const ptrdiff_t rdelta = reinterpret_cast<const uint8_t*>(a.residual) - reinterpret_cast<const uint8_t*>(a.dst);
+    uint32_t raddr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t q = ((uint32_t)lane >> 2) + 8u * k;
+        raddr[k] = stg + q * 64u + ((c ^ ((q >> 1) & 3u)) << 4);
+    }
+    for (int n0 = 0; n0 < a.n_pad; n0 += 16) {
+        uint32_t r0[16];
+        tmem_ld16_nowait(trow + (uint32_t)n0, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (uint32_t cc = 0; cc < 4; ++cc) {
+            const float x0 = __uint_as_float(r0[4 * cc]) + bias_s[n0 + 4 * cc], x1 = __uint_as_float(r0[4 * cc + 1]) + bias_s[n0 + 4 * cc + 1];
+            const float x2 = __uint_as_float(r0[4 * cc + 2]) + bias_s[n0 + 4 * cc + 2], x3 = __uint_as_float(r0[4 * cc + 3]) + bias_s[n0 + 4 * cc + 3];
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow + ((cc ^ wsw) << 4)), "r"(__float_as_uint(x0)),
+                         "r"(__float_as_uint(x1)), "r"(__float_as_uint(x2)), "r"(__float_as_uint(x3))
+                         : "memory");
+        }
+        __syncwarp();
+        const bool col_ok = n0 + (int)c * 4 + 4 <= a.Cout;
+        const size_t boff = ((size_t)n0 + (size_t)c * 4) * (OUT_F16 ? 2 : 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(raddr[k]) : "memory");
+            if (qlive[k] && col_ok) {
+                uint8_t* o = qptr[k] + boff;
+                float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+                if (OUT_F16) {
+                    const uint2 rr = *reinterpret_cast<const uint2*>(o + rdelta);
+                    const float2 ra = __half22float2(*reinterpret_cast<const __half2*>(&rr.x)), rb = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+                    x[0] += ra.x; x[1] += ra.y; x[2] += rb.x; x[3] += rb.y;
+                } else {
+                    const float4 rr = *reinterpret_cast<const float4*>(o + rdelta);
+                    x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    x[j] = fmaxf(x[j], slope * x[j]);
+                    if (a.round_out) x[j] = __uint_as_float((__float_as_uint(x[j]) + 0x1000u) & 0xFFFFE000u);
+                }
+                if (OUT_F16) {
+                    uint2 ov;
+                    *reinterpret_cast<__half2*>(&ov.x) = __floats2half2_rn(x[0], x[1]);
+                    *reinterpret_cast<__half2*>(&ov.y) = __floats2half2_rn(x[2], x[3]);
+                    *reinterpret_cast<uint2*>(o) = ov;
+                } else {
+                    *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // One tile of the staged epilogue for a warp (TMEM lane quadrant q): output pointers / liveness of the 4 pixels each lane
 // stores for, then the 64-byte steps; tiles are kTW x kTH pixels with accumulator row p = y * kTW + x.  Layers the staged
 // path cannot take (unaligned channel slices, the rare activations) go through the generic out-of-line epilogue.
@@ -361,7 +427,10 @@ __device__ __forceinline__ void staged_tile(const TcArgs& a, const float* bias_s
                                     a.dst_c + a.dst_coff;
             qptr[k] = reinterpret_cast<uint8_t*>(a.dst) + qidx * esize;
         }
-        if (a.out_f16) epilogue_staged<true, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+        if (a.residual != nullptr) {
+            if (a.out_f16) epilogue_staged_res<true>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+            else epilogue_staged_res<false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+        } else if (a.out_f16) epilogue_staged<true, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
         else if (a.round_out) epilogue_staged<false, true>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
         else epilogue_staged<false, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
     } else {
@@ -747,7 +816,7 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream) {
+static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, int n_pad, int k_pad, int round_out, void* stream) {
     MR_REQUIRE(desc != nullptr, "mr_conv2d_nhwc_tc: null descriptor");
     const mr_conv_desc& d = *desc;
     MR_REQUIRE(d.n_src >= 1 && d.n_src <= MR_CONV_MAX_SRC, "mr_conv2d_nhwc_tc: n_src=%d out of range", d.n_src);
@@ -902,6 +971,14 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     a.dst_H = d.dst_H; a.dst_W = d.dst_W; a.dst_c = d.dst_c; a.dst_coff = d.dst_coff;
     a.oy_step = d.oy_step; a.ox_step = d.ox_step; a.oy_off = d.oy_off; a.ox_off = d.ox_off;
     a.act = d.act; a.act_a = d.act_a; a.act_b = d.act_b; a.round_out = round_out;
+    a.residual = residual;
+    if (residual != nullptr) {
+        const int vm = a.out_f16 ? 7 : 3;
+        MR_REQUIRE(kStagedEpi, "mr_conv2d_nhwc_tc: a residual input needs the staged epilogue (MONOREC_B200_TC_EPI=1)");
+        MR_REQUIRE(((d.dst_c | d.dst_coff | d.Cout) & vm) == 0 && !(a.out_f16 && round_out) && (d.act == MR_ACT_NONE || d.act == MR_ACT_LEAKY) &&
+                       (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                   "mr_conv2d_nhwc_tc: residual epilogue needs 16-byte aligned channel slices and a none/leaky activation");
+    }
     if (halo) {
         a.stages = halo_stages;
         const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
@@ -940,4 +1017,13 @@ extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad,
     }
     MR_LAUNCH_CHECK("conv_tc_kernel");
     return MR_OK;
+}
+
+extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream) {
+    return conv2d_nhwc_tc_impl(desc, nullptr, n_pad, k_pad, round_out, stream);
+}
+
+extern "C" int mr_conv2d_nhwc_tc_res(const mr_conv_desc* desc, const void* residual, int n_pad, int k_pad, int round_out, void* stream) {
+    MR_REQUIRE(residual != nullptr, "mr_conv2d_nhwc_tc_res: null residual");
+    return conv2d_nhwc_tc_impl(desc, residual, n_pad, k_pad, round_out, stream);
 }
