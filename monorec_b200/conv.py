@@ -173,11 +173,30 @@ def nchw_to_nhwc(x, out=None, out_coff=0, one_minus=None, dtype=None):
     return out
 
 
+def as_nhwc(x, dtype):
+    """(B,C,H,W) feature map -> NHWC tensor of `dtype`: a view when the memory is already channels-last in that type."""
+    v = x.permute(0, 2, 3, 1)
+    if x.dtype == dtype and v.is_contiguous():
+        return v
+    return nchw_to_nhwc(x.to(torch.float32), dtype=dtype)
+
+
 def maxpool2(x):
     lib = _lib.load()
     B, H, W, C = x.shape
     out = torch.empty(B, H // 2, W // 2, C, device=x.device, dtype=x.dtype)
     fn, name = (lib.mr_maxpool2_nhwc_f16, "mr_maxpool2_nhwc_f16") if x.dtype == torch.float16 else (lib.mr_maxpool2_nhwc, "mr_maxpool2_nhwc")
+    with torch.cuda.device(x.device):
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream(x)), name)
+    return out
+
+
+def maxpool3s2(x):
+    """nn.MaxPool2d(3, stride=2, padding=1) on NHWC (the ResNet stem's pooling)."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, C, device=x.device, dtype=x.dtype)
+    fn, name = (lib.mr_maxpool3s2_nhwc_f16, "mr_maxpool3s2_nhwc_f16") if x.dtype == torch.float16 else (lib.mr_maxpool3s2_nhwc, "mr_maxpool3s2_nhwc")
     with torch.cuda.device(x.device):
         _lib.check(fn(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream(x)), name)
     return out
@@ -264,19 +283,24 @@ class PackedConv:
                                              allow_k32=HALO_K32 or not (HALO_F16 and tuple(self.stride) == (1, 1)))
         return self._wtc[half]
 
-    def __call__(self, srcs, out=None, out_hw=None, final=False):
+    def __call__(self, srcs, out=None, out_hw=None, final=False, residual=None, out_coff=0):
+        """residual: tensor shaped like the output, added before the activation (tensor-core path, staged epilogue only);
+        out_coff: first channel of the slice of `out` this layer writes."""
         assert tuple(s.shape[3] for s in srcs) == self.src_c, (tuple(s.shape[3] for s in srcs), self.src_c)
         if MODE == "f16" and srcs[0].dtype == torch.float16:
             if self.tc_ok_f16:
-                return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=False, half=True, out_f32=final)
+                return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=False, half=True, out_f32=final,
+                                 residual=residual, out_coff=out_coff)
             assert self.cout == 1, "f16 mode: only the single-channel heads run on the CUDA-core kernel"
         if MODE == "tf32" and self.tc_ok:
-            return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=not final)
+            return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=not final, residual=residual, out_coff=out_coff)
+        if residual is not None or out_coff:
+            raise NotImplementedError("monorec_b200.conv: residual inputs / channel-slice outputs need the tensor-core path")
         return conv2d(srcs, self.w32, self.bias, self.kh, self.kw, stride=self.stride, act=self.act, act_a=self.act_a,
                       act_b=self.act_b, out=out, pad=self.pad, out_hw=out_hw, out_step=self.out_step, out_off=self.out_off)
 
 
-def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f32=False):
+def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f32=False, residual=None, out_coff=0):
     """Tensor-core launch (csrc/conv_tc.cu) of a PackedConv."""
     lib = _lib.load()
     x0 = srcs[0]
@@ -303,12 +327,17 @@ def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f3
     d.weight = wtc.data_ptr()
     d.bias = L.bias.data_ptr() if L.bias is not None else None
     d.dst = out.data_ptr()
-    d.dst_H, d.dst_W, d.dst_c, d.dst_coff = out.shape[1], out.shape[2], out.shape[3], 0
+    d.dst_H, d.dst_W, d.dst_c, d.dst_coff = out.shape[1], out.shape[2], out.shape[3], int(out_coff)
     d.oy_step, d.ox_step, d.oy_off, d.ox_off = L.out_step[0], L.out_step[1], L.out_off[0], L.out_off[1]
     d.act, d.act_a, d.act_b = L.act, L.act_a, L.act_b
     d.src_dtype, d.dst_dtype = (DT_F16 if half else DT_F32), _dt(out)
     with torch.cuda.device(x0.device):
-        _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
+        if residual is None:
+            _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
+        else:
+            assert residual.shape == out.shape and residual.dtype == out.dtype and residual.is_contiguous() and residual.is_cuda
+            _lib.check(lib.mr_conv2d_nhwc_tc_res(ctypes.byref(d), residual.data_ptr(), n_pad, k_pad, int(round_out), _stream(x0)),
+                       "mr_conv2d_nhwc_tc_res")
     return out
 
 
