@@ -265,7 +265,8 @@ __device__ __forceinline__ void epilogue_row_quad(uint32_t trow, const TcArgs& a
 }
 
 // out-of-line copy of the generic epilogue for the staged kernel's rare fallback (keeps its hot code small)
-__device__ __noinline__ void epilogue_row_outofline(uint32_t trow, const TcArgs& a, const float* bias_s, float* op, bool live, bool vec_ok) {
+// (`a` by value: a reference would force the kernel's parameter block onto the local stack for the hot path as well)
+__device__ __noinline__ void epilogue_row_outofline(uint32_t trow, const TcArgs a, const float* bias_s, float* op, bool live, bool vec_ok) {
     epilogue_row(trow, a, bias_s, op, live, vec_ok);
 }
 
