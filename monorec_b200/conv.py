@@ -28,6 +28,9 @@ MODE = os.environ.get("MONOREC_B200_CONV", "tf32").lower()
 K32 = os.environ.get("MONOREC_B200_TC_K32", "1") != "0"
 HALO_F16 = os.environ.get("MONOREC_B200_TC_HALO_F16", "1") != "0" and os.environ.get("MONOREC_B200_TC_HALO", "") != "0"
 HALO_K32 = os.environ.get("MONOREC_B200_TC_HALO_K32", "0") != "0"   # experimental: 64-byte rows inside the halo box as well
+# experimental: the single-channel layers (1x1 mask classifier, the four 3x3 depth heads) on the tensor cores too (Cout padded
+# to 16) instead of the CUDA-core per-pixel kernel, which takes 0.45 ms of a half-mode forward
+TC_HEADS = os.environ.get("MONOREC_B200_TC_HEADS", "0") != "0"
 DT_F32, DT_F16 = 0, 1
 
 
@@ -272,7 +275,7 @@ class PackedConv:
         self.act, self.act_a, self.act_b = act, act_a, act_b
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
         self.w32 = pack_conv_weight(w)
-        self.tc_ok = allow_tc and self.cout <= 256 and self.cout >= 8 and all(c % 4 == 0 for c in self.src_c)
+        self.tc_ok = (allow_tc or TC_HEADS) and self.cout <= 256 and (self.cout >= 8 or TC_HEADS) and all(c % 4 == 0 for c in self.src_c)
         self.tc_ok_f16 = self.tc_ok and all(c % 8 == 0 for c in self.src_c)
         self._wtc = {}
         self._w_src = w
