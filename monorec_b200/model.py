@@ -20,6 +20,9 @@ __all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "Res
 
 # experimental: ResNet trunk on the conv engine; needs the staged epilogue of the tensor-core kernels for the residual adds
 TRUNK_ENGINE = os.environ.get("MONOREC_B200_TRUNK", "cudnn").lower() == "engine"
+# experimental: in half mode run the cuDNN trunk in half as well (folded weights and activations), so that its NHWC outputs feed
+# the conv engine without casts
+TRUNK_CUDNN_F16 = os.environ.get("MONOREC_B200_TRUNK", "cudnn").lower() == "cudnn_f16"
 if TRUNK_ENGINE and os.environ.get("MONOREC_B200_TC_EPI", "0") != "1":
     raise RuntimeError("MONOREC_B200_TRUNK=engine needs MONOREC_B200_TC_EPI=1 (residual adds live in the staged epilogue)")
 
@@ -136,6 +139,15 @@ class ResnetEncoder(nn.Module):
         import torch.nn.functional as F
         e, f = self.encoder, self._folded()
         x = (input_image - 0.45) / 0.225
+        if TRUNK_CUDNN_F16 and C.MODE == "f16" and x.is_cuda:
+            if getattr(self, "_fold_half_sig", None) != self._fold_sig:
+                conv = lambda wb: (wb[0].half().contiguous(memory_format=torch.channels_last), wb[1].half())   # noqa: E731
+                self._fold_half = {"stem": conv(f["stem"]),
+                                   "blocks": [[(conv(a), s_, conv(b), None if d is None else conv(d[:2]) + (d[2],)) for a, s_, b, d in blocks]
+                                              for blocks in f["blocks"]]}
+                self._fold_half_sig = self._fold_sig
+            f = self._fold_half
+            x = x.half()
         x = F.conv2d(x, *f["stem"], stride=e.conv1.stride, padding=e.conv1.padding).relu_()
         self.features = [x]
         x = e.maxpool(x)
