@@ -14,6 +14,7 @@ Files written
                           uint8 inputs + reference CostVolumeModule outputs (sub-sampled volumes, full argmax,
                           valid masks, per-plane float64 checksums)
   cv_synth_small.npz      full reference cost-volume tensors for small seeded synthetic configs
+  cv_synth_d64f6.npz      the same for 64 planes x 6 source frames (`--only-d64f6`)
   model_synth_small.npz   full MonoRecModel forward (seeded weights, 2 gains) on a small synthetic config:
                           cv_mask, 4 depth maps, image_features checksums
 """
@@ -121,10 +122,31 @@ def top2_margin(cv):
     return (t[:, 0] - t[:, 1])
 
 
+def write_small(path, ref_mod, configs):
+    """Full reference cost-volume tensors for small seeded synthetic configs {tag: (B, F, D, H, W, seed)}."""
+    small = {}
+    for tag, (B, nF, D, H, W, seed) in configs.items():
+        d = make_inputs(B, nF, H, W, seed=seed)
+        cv, sf = run_ref_cv(ref_mod, d, steps=D)
+        small[f"{tag}_cfg"] = np.array([B, nF, D, H, W, seed])
+        small[f"{tag}_cv"] = cv.numpy()
+        small[f"{tag}_sf"] = np.stack([v.numpy() for v in sf])
+        small[f"{tag}_key_u8"] = np.round((d["keyframe"].numpy() + 0.5) * 255).astype(np.uint8)
+        small[f"{tag}_frames_u8"] = np.round((torch.stack(d["frames"]).numpy() + 0.5) * 255).astype(np.uint8)
+        small[f"{tag}_poses"] = torch.stack(d["poses"]).numpy()
+        small[f"{tag}_K"] = d["keyframe_intrinsics"].numpy()
+    np.savez_compressed(path, **small)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref_mod = import_reference()
+    if "--only-d64f6" in sys.argv:
+        # BASELINE config 5's plane and frame counts (64 planes, 6 source frames) at a small size; added after the other
+        # files, which are left untouched
+        write_small(HERE / "cv_synth_d64f6.npz", ref_mod, {"d": (1, 6, 64, 40, 72, 4)})
+        return
 
     # ---- 1. bundled KITTI sample --------------------------------------------------------------
     s = load_kitti_sample()

@@ -25,7 +25,7 @@ def kitti_sample_dict():
 
 
 def synth_small_dict(tag):
-    g = np.load(GOLDEN / "cv_synth_small.npz")
+    g = np.load(GOLDEN / ("cv_synth_d64f6.npz" if tag == "d" else "cv_synth_small.npz"))
     B, nF, D, H, W, seed = [int(v) for v in g[f"{tag}_cfg"]]
     K = torch.from_numpy(g[f"{tag}_K"])
     data = {"keyframe": u8_to_img(g[f"{tag}_key_u8"]),

@@ -94,3 +94,13 @@ def test_engine_trunk_matches_cudnn_trunk(mode, tol):
             assert a.shape == b.shape and _rel(b.float().cpu(), a.cpu()) < tol
     finally:
         K.set_mode(old)
+
+
+def test_cost_volume_golden_d64_f6():
+    """CUDA cost volume vs the reference's own output for 64 planes x 6 source frames (tests/golden/cv_synth_d64f6.npz); the
+    same gates as tests/test_cost_volume_gpu.py::test_golden_small_full_tensors -- moves there once it has run on a GPU."""
+    from tests.helpers import compare_volumes, synth_small_dict
+    from tests.test_cost_volume_gpu import _run
+    data, D, ref_cv, ref_sf = synth_small_dict("d")
+    cv, sf = _run(data, steps=D)
+    print(compare_volumes(cv, sf, ref_cv, ref_sf))

@@ -7,7 +7,7 @@ from oracle import cost_volume_oracle as O
 from tests.helpers import compare_volumes, kitti_sample_dict, synth_small_dict
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])   # "d": 64 planes x 6 source frames (BASELINE config 5's counts)
 def test_torch_restatement_matches_reference_small(tag):
     data, D, ref_cv, ref_sf = synth_small_dict(tag)
     cv, sf = O.cost_volume_torch(data, steps=D)
@@ -17,7 +17,7 @@ def test_torch_restatement_matches_reference_small(tag):
         assert (a - r).abs().max().item() <= 5e-5
 
 
-@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
 def test_closed_form_matches_reference_small(tag):
     data, D, ref_cv, ref_sf = synth_small_dict(tag)
     cv, sf, valid, _ = O.cost_volume_closed_form(data, steps=D, dtype=np.float32)
