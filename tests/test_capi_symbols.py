@@ -39,3 +39,33 @@ def test_product_never_imports_oracle():
     pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
     for p in (ROOT / "monorec_b200").rglob("*.py"):
         assert not pat.search(p.read_text()), f"{p} imports the oracle"
+
+
+def test_header_is_plain_c_and_a_c_consumer_links(tmp_path):
+    """include/monorec_b200.h compiles as C99 (-pedantic) and a C program links against the library and reaches the
+    argument checks without a GPU (no compute call)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    import pytest
+    from monorec_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    _lib.load()
+    root = Path(__file__).resolve().parent.parent
+    src = tmp_path / "consumer.c"
+    src.write_text('#include "monorec_b200.h"\n#include <stdio.h>\n#include <string.h>\n'
+                   'int main(void) {\n'
+                   '    mr_conv_desc d; memset(&d, 0, sizeof d);\n'
+                   '    if (mr_sizeof_conv_desc() != (int)sizeof d) return 2;\n'
+                   '    if (mr_conv2d_nhwc_tc(0, 16, 32, 0, 0) == MR_OK) return 3;\n'
+                   '    if (strstr(mr_last_error(), "null descriptor") == 0) return 4;\n'
+                   '    if (mr_cost_volume_workspace_bytes(8, 4, 256, 512) <= 0) return 5;\n'
+                   '    printf("%d\\n", mr_version());\n    return 0;\n}\n')
+    exe = tmp_path / "consumer"
+    libdir = _lib.LIB_PATH.parent
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", f"-I{root / 'include'}", str(src), "-o", str(exe),
+                    f"-L{libdir}", f"-l:{_lib.LIB_PATH.name}", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert int(out.stdout.strip()) == _lib.load().mr_version()
