@@ -5,11 +5,12 @@
 #      (MONOREC_B200_TC_HALO_K32=1), 8 epilogue warps over 4 accumulators in the single-CTA halo kernel
 #      (MONOREC_B200_TC_HALO_EPI8=1), and their combinations
 mkdir -p gpurun_out
+exec > >(tee gpurun_out/next_round.log) 2>&1
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ubench_tc tools/ubench_tc.cu && timeout 300 /tmp/ubench_tc > gpurun_out/ubench_tc.txt 2>&1; tail -5 gpurun_out/ubench_tc.txt
 run() {  # name, env assignments...
   local name=$1; shift
   echo "== $name"
-  env "$@" timeout 600 python -m pytest tests/test_convnet_gpu.py -x -q 2>&1 | tail -1
+  env "$@" timeout 600 python -m pytest tests/test_convnet_gpu.py -x -q 2>&1 | tail -4
   for m in f16 tf32; do echo -n "$m: "; env "$@" MONOREC_B200_CONV=$m timeout 200 python tools/profile_model.py 8 4 10 2>&1 | tail -1; done
   env "$@" MONOREC_B200_CONV=f16 timeout 200 python tools/bench_conv_layers.py 2>&1 | tail -7
 }
