@@ -327,12 +327,12 @@ def main():
             gm = GraphedMonoRec(model, sets[0])
             fm_steps = 20
             for i in range(3):
-                all_gather_batch(gm(sets[i % NSETS])["result"])
+                all_gather_batch(gm(sets[i % NSETS])["result"], equal_shards=True)
             barrier()
             f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             f0.record()
             for i in range(fm_steps):
-                res = all_gather_batch(gm(sets[i % NSETS])["result"])
+                res = all_gather_batch(gm(sets[i % NSETS])["result"], equal_shards=True)
             f1.record()
             barrier()
             t = torch.tensor([f0.elapsed_time(f1)], device=dev)

@@ -30,12 +30,17 @@ def shard_data_dict(data, rank, world):
     return out
 
 
-def all_gather_batch(t, group=None):
+def all_gather_batch(t, group=None, equal_shards=False):
     """All-gather of per-rank (b_r, ...) maps into (sum b_r, ...) on every rank (one ncclAllGather when the shards
-    are equal, a padded gather otherwise)."""
+    are equal, a padded gather otherwise).  `equal_shards=True` asserts the caller knows every rank holds the same b_r
+    (a batch divisible by the world size) and skips the size exchange and its host synchronisation."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t
     world = dist.get_world_size(group)
+    if equal_shards:
+        out = t.new_empty((world * t.shape[0],) + tuple(t.shape[1:]))
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
     sizes = torch.tensor([t.shape[0]], device=t.device, dtype=torch.int64)
     all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
     dist.all_gather(all_sizes, sizes, group=group)

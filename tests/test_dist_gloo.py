@@ -27,6 +27,8 @@ def _worker(rank, world, port, batch, q):
     res = mine["keyframe"].mean(1, keepdim=True)
     full = all_gather_batch(res)
     ok = torch.equal(full, data["keyframe"].mean(1, keepdim=True))
+    if batch % world == 0:   # the no-size-exchange fast path gives the same tensor
+        ok = ok and torch.equal(all_gather_batch(res, equal_shards=True), full)
     q.put((rank, bool(ok), tuple(full.shape)))
     dist.destroy_process_group()
 
