@@ -15,6 +15,7 @@ Files written
                           valid masks, per-plane float64 checksums)
   cv_synth_small.npz      full reference cost-volume tensors for small seeded synthetic configs
   cv_synth_d64f6.npz      the same for 64 planes x 6 source frames (`--only-d64f6`)
+  model_kitti_sample.npz  full MonoRecModel forward on the bundled KITTI sample, seeded weights (`--only-kitti-model`)
   model_synth_small.npz   full MonoRecModel forward (seeded weights, 2 gains) on a small synthetic config:
                           cv_mask, 4 depth maps, image_features checksums
 """
@@ -142,6 +143,26 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref_mod = import_reference()
+    if "--only-kitti-model" in sys.argv:
+        # the north-star sentence literally: full MonoRecModel on the bundled example sample (256x512, 2 source frames);
+        # no pretrained weights exist offline, so seeded weights (two gains) as in model_synth_small.npz
+        s = load_kitti_sample()
+        out = {}
+        for gain_tag, gain in (("g1", 1.0), ("g07", 0.7)):
+            model = ref_mod.MonoRecModel()
+            model.load_state_dict(seeded_state_dict(model, seed=7, gain=gain))
+            model.eval()
+            with torch.no_grad():
+                r = model(sample_to_dict(s))
+            out[f"{gain_tag}_cv_mask"] = r["cv_mask"].numpy().astype(np.float16)        # values in (0,1): 5e-4 quantisation
+            out[f"{gain_tag}_result"] = r["result"].numpy()                             # fp32: the gated quantity
+            for i, p in enumerate(r["predicted_inverse_depths"][1:], start=1):
+                out[f"{gain_tag}_depth{i}"] = p.numpy()
+            print(gain_tag, "result range", float(r["result"].min()), float(r["result"].max()),
+                  "mask range", float(r["cv_mask"].min()), float(r["cv_mask"].max()))
+        out["wseed"] = np.array([7])
+        np.savez_compressed(HERE / "model_kitti_sample.npz", **out)
+        return
     if "--only-d64f6" in sys.argv:
         # BASELINE config 5's plane and frame counts (64 planes, 6 source frames) at a small size; added after the other
         # files, which are left untouched

@@ -104,3 +104,32 @@ def test_cost_volume_golden_d64_f6():
     data, D, ref_cv, ref_sf = synth_small_dict("d")
     cv, sf = _run(data, steps=D)
     print(compare_volumes(cv, sf, ref_cv, ref_sf))
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-3), ("tf32", 1e-3), ("f16", 1e-3)])
+@pytest.mark.parametrize("gain_tag,gain", [("g1", 1.0), ("g07", 0.7)])
+def test_full_model_on_bundled_sample(mode, tol, gain_tag, gain):
+    """|delta inverse depth| < 1e-3 against the unmodified reference on the bundled KITTI sample (tests/golden/model_kitti_sample.npz,
+    seeded weights): the north-star parity sentence on the CUDA path.  Moves to the regular suite once it has run on a GPU."""
+    import numpy as np
+    from monorec_b200 import conv as K
+    from monorec_b200.model import MonoRecModel
+    from monorec_b200.synthetic import seeded_state_dict, to_device
+    from tests.helpers import GOLDEN, kitti_sample_dict
+    g = np.load(GOLDEN / "model_kitti_sample.npz")
+    data, _ = kitti_sample_dict()
+    old = K.MODE
+    K.set_mode(mode)
+    try:
+        model = MonoRecModel()
+        model.load_state_dict(seeded_state_dict(model, seed=int(g["wseed"][0]), gain=gain))
+        model = model.to(DEV).eval()
+        with torch.no_grad():
+            out = model(to_device(data, DEV))
+        torch.cuda.synchronize()
+        dres = np.abs(out["result"].float().cpu().numpy() - g[f"{gain_tag}_result"]).max()
+        dmask = np.abs(out["cv_mask"].float().cpu().numpy() - g[f"{gain_tag}_cv_mask"].astype(np.float32)).max()
+        print(mode, gain_tag, "result", dres, "mask", dmask)
+        assert dres < tol and dmask < 5e-3
+    finally:
+        K.set_mode(old)

@@ -65,3 +65,22 @@ def test_convnet_oracle_matches_reference_model(gain_tag, gain):
     assert np.abs(out["cv_mask"].numpy() - g[f"{gain_tag}_cv_mask"]).max() < 2e-5
     for i, p in enumerate(out["predicted_inverse_depths"]):
         assert np.abs(p.numpy() - g[f"{gain_tag}_depth{i}"]).max() < 2e-5, i
+
+
+@pytest.mark.parametrize("gain_tag,gain", [("g1", 1.0), ("g07", 0.7)])
+def test_oracle_matches_reference_model_on_bundled_sample(gain_tag, gain):
+    """The north-star parity sentence at the oracle level: full MonoRecModel on example/data's KITTI sample (256x512, 2 source
+    frames, seeded weights) -- cost-volume oracle + conv-stack oracle vs the unmodified reference (model_kitti_sample.npz)."""
+    from monorec_b200.model import MonoRecModel
+    from monorec_b200.synthetic import seeded_state_dict
+    from oracle import convnet_oracle as CO
+    from tests.helpers import GOLDEN
+    g = np.load(GOLDEN / "model_kitti_sample.npz")
+    data, _ = kitti_sample_dict()
+    cv, sf = O.cost_volume_torch(data)
+    out = CO.monorec_forward(seeded_state_dict(MonoRecModel(), seed=int(g["wseed"][0]), gain=gain), data, cv, sf)
+    assert np.abs(out["result"].numpy() - g[f"{gain_tag}_result"]).max() < 2e-5
+    assert np.abs(out["cv_mask"].numpy() - g[f"{gain_tag}_cv_mask"].astype(np.float32)).max() < 6e-4   # stored as fp16
+    for i, p in enumerate(out["predicted_inverse_depths"]):
+        if i > 0:
+            assert np.abs(p.numpy() - g[f"{gain_tag}_depth{i}"]).max() < 2e-5, i
