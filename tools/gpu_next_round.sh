@@ -22,6 +22,8 @@ run "staged epilogue + 64-byte halo rows" MONOREC_B200_TC_EPI=1 MONOREC_B200_TC_
 run "staged epilogue + 64-byte halo rows + 8-warp halo epilogue" MONOREC_B200_TC_EPI=1 MONOREC_B200_TC_HALO_K32=1 MONOREC_B200_TC_HALO_EPI8=1
 run "single-channel heads on the tensor cores" MONOREC_B200_TC_HEADS=1
 run "cuDNN trunk in half (half mode only)" MONOREC_B200_TRUNK=cudnn_f16
+echo "== staged goldens on the DEFAULT path: bundled-sample full model, 64 planes x 6 frames"
+MONOREC_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -q -m gpu -s -k "bundled or d64 or maxpool" 2>&1 | tail -12
 echo "== experimental pieces: 3x3/s2 max-pool, residual epilogue, ResNet trunk on the engine"
 MONOREC_B200_EXPERIMENTAL=1 MONOREC_B200_TC_EPI=1 timeout 600 python -m pytest tests/test_experimental_gpu.py -q -m gpu 2>&1 | tail -3
 for m in f16 tf32; do echo -n "engine trunk $m: "; MONOREC_B200_TC_EPI=1 MONOREC_B200_TRUNK=engine MONOREC_B200_CONV=$m timeout 200 python tools/profile_model.py 8 4 10 2>&1 | tail -1; done
