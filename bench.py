@@ -212,8 +212,6 @@ def main():
     depths = torch.empty(D, device=dev)
     cv = torch.empty(B, D, H, W, device=dev)
     sfcv = torch.empty(F, B, D, H, W, device=dev)
-    ws_bytes_k1 = lib.mr_cost_volume_workspace_bytes(B, F, H, W)      # (r,g,b,0)-packed copies of the source frames
-    ws_k1 = torch.empty(ws_bytes_k1, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     k_start = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k_stop = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -225,9 +223,9 @@ def main():
                                             proj.data_ptr(), depths.data_ptr(), D, INV_LO, INV_HI, stream), "tables")
         if timed_idx is not None:
             k_start[timed_idx].record()
-        _lib.check(lib.mr_cost_volume_fwd_ws(d["keyframe"].data_ptr(), _lib.ptr_array(d["frames"]), proj.data_ptr(),
-                                             depths.data_ptr(), cv.data_ptr(), sfcv.data_ptr(), B, F, D, H, W, 10.0, None,
-                                             ws_k1.data_ptr(), ws_bytes_k1, stream), "cost volume")
+        _lib.check(lib.mr_cost_volume_fwd(d["keyframe"].data_ptr(), _lib.ptr_array(d["frames"]), proj.data_ptr(),
+                                          depths.data_ptr(), cv.data_ptr(), sfcv.data_ptr(), B, F, D, H, W, 10.0, None,
+                                          stream), "cost volume")
         if timed_idx is not None:
             k_stop[timed_idx].record()
 
@@ -271,7 +269,7 @@ def main():
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": k1_traffic(), "peak_source": f"{peak_src} (burst copy)",
-                             "kernel": "cost_volume_kernel (+ its 30 us source re-layout launch: the events bracket mr_cost_volume_fwd_ws)",
+                             "kernel": "cost_volume_kernel (the events bracket mr_cost_volume_fwd: one launch)",
                              "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_KEYFRAME * B},
                 "clocks": clocks.summary()}

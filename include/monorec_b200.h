@@ -67,6 +67,8 @@ int mr_projection_tables(const float* keyframe_pose, const float* keyframe_K,
  *   out_sfcv      [F,B,D,H,W]    data_dict["single_frame_cvs"][f] = out_sfcv[f]
  *   alpha         view-weight sharpness (reference: 10), chan_w[3] channel weights (reference: 5/32,16/32,11/32)
  * Constraints: 1 <= F <= MR_MAX_FRAMES, 2 <= D <= 128, H >= 5, W >= 5.
+ * The source frames are read through TMA (cp.async.bulk.tensor boxes of the NCHW frames into shared-memory windows shared by
+ * runs of consecutive depth planes); the frames must stay unmodified until the kernel has finished (stream order).
  */
 int mr_cost_volume_fwd(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
                        float* out_cv, float* out_sfcv,
@@ -74,14 +76,14 @@ int mr_cost_volume_fwd(const float* keyframe, const float* const* frames, const 
                        float alpha, const float* chan_w /* host, 3 floats, NULL = reference default */,
                        void* stream);
 
-/* The same kernel with a caller-owned device workspace of mr_cost_volume_workspace_bytes(B,F,H,W) bytes (16-byte aligned):
- * the source frames are first re-laid as (r,g,b,0) pixels so that every bilinear tap is one 16-byte load (the gather stage
- * is bound by L1/LSU requests); results are bit-identical to mr_cost_volume_fwd. */
-long long mr_cost_volume_workspace_bytes(int B, int F, int H, int W);
-int mr_cost_volume_fwd_ws(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
-                          float* out_cv, float* out_sfcv,
-                          int B, int F, int D, int H, int W,
-                          float alpha, const float* chan_w, void* workspace, long long workspace_bytes, void* stream);
+/* The same kernel with the TMA window staging switched off: every bilinear tap is a global-memory load (what
+ * mr_cost_volume_fwd itself does for frames TMA cannot address: W % 4 != 0 or a base that is not 16-byte aligned, and for
+ * the few (frame, plane) units whose source footprint does not fit a shared-memory window).  Same results up to the
+ * last-bit differences of the two interpolation code paths; kept callable for tests and A/B timing. */
+int mr_cost_volume_fwd_gather(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
+                              float* out_cv, float* out_sfcv,
+                              int B, int F, int D, int H, int W,
+                              float alpha, const float* chan_w, void* stream);
 
 /* Same path with HOST buffers (pinned or pageable): uploads the images and matrices, runs
  * mr_projection_tables + mr_cost_volume_fwd and downloads both volumes; batch elements are pipelined on

@@ -6,8 +6,11 @@ import ctypes
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libmonorec_b200.so"
+# MONOREC_B200_LIB: load another build of the library (kernel-variant experiments: tools/build_variant.py)
+LIB_PATH = Path(os.environ["MONOREC_B200_LIB"]) if os.environ.get("MONOREC_B200_LIB") else _PKG / "libmonorec_b200.so"
 _lib = None
 
 c_float_p = POINTER(c_float)
@@ -21,9 +24,8 @@ SIGNATURES = {
                                      c_int, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
     "mr_cost_volume_fwd": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_int, c_int, c_float, c_float_p, c_void_p]),
-    "mr_cost_volume_workspace_bytes": (c_longlong, [c_int, c_int, c_int, c_int]),
-    "mr_cost_volume_fwd_ws": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                      c_int, c_int, c_int, c_float, c_float_p, c_void_p, c_longlong, c_void_p]),
+    "mr_cost_volume_fwd_gather": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                          c_int, c_int, c_int, c_int, c_float, c_float_p, c_void_p]),
     "mr_cost_volume_host_workspace": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
     "mr_cost_volume_host": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float] * 3 + [c_void_p, c_longlong]),
     "mr_conv2d_nhwc": (c_int, [c_void_p, c_void_p]),
@@ -52,7 +54,8 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists() and build_if_missing:
+    if build_if_missing and not os.environ.get("MONOREC_B200_LIB"):
+        # no-op when the source digest matches the stamp; rebuilds a stale library (sources newer than the .so)
         from . import build as _build
         _build.build()
     if not LIB_PATH.exists():

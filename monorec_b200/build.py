@@ -38,10 +38,13 @@ def build(force=False, verbose=False):
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == dig:
         return LIB
     if not Path(NVCC).exists():
-        if LIB.exists():
-            # GPU box without a matching source digest but with a prebuilt library: use what travelled.
+        if LIB.exists() and os.environ.get("MONOREC_B200_ALLOW_STALE") == "1":
+            import warnings
+            warnings.warn(f"{LIB.name} does not match the sources (digest mismatch) and nvcc is missing: using the stale "
+                          "library because MONOREC_B200_ALLOW_STALE=1")
             return LIB
-        raise RuntimeError(f"nvcc not found at {NVCC} and no prebuilt {LIB.name}")
+        raise RuntimeError(f"nvcc not found at {NVCC} and {LIB.name} is missing or older than the sources "
+                           "(set MONOREC_B200_ALLOW_STALE=1 to load a stale library anyway)")
     cmd = [NVCC, *FLAGS, "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
     if verbose:
         cmd += ["-Xptxas", "-v"]

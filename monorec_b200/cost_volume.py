@@ -39,8 +39,8 @@ class CostVolumeModule(nn.Module):
         self.alpha = alpha
         self.not_center_cv = not_center_cv
         self.sfcv_mult_mask = sfcv_mult_mask
-        # gather through (r,g,b,0)-packed copies of the source frames (one 16-byte load per tap); False = planar gather
-        self.packed_gather = os.environ.get("MONOREC_B200_CV_PACKED", "1") != "0"
+        # False: bilinear taps straight from global memory instead of TMA-staged shared-memory windows (tests, A/B timing)
+        self.tma_windows = os.environ.get("MONOREC_B200_CV_TMA", "1") != "0"
         if not (use_ssim is True or use_ssim == 1) or isinstance(use_ssim, float):
             raise NotImplementedError("monorec_b200: only use_ssim=True is implemented (reference default)")
         if patch_size != 3 or not_center_cv or not sfcv_mult_mask:
@@ -94,17 +94,9 @@ class CostVolumeModule(nn.Module):
                 cw = (_lib.c_float * 3)(*self.channel_weights)
             else:
                 cw = (_lib.c_float * 3)(1 / 3, 1 / 3, 1 / 3)  # monorec_model.py:174-177
-            if self.packed_gather:
-                ws_bytes = lib.mr_cost_volume_workspace_bytes(B, F, H, W)
-                ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-                _lib.check(lib.mr_cost_volume_fwd_ws(keyframe.data_ptr(), _lib.ptr_array(frames), proj.data_ptr(),
-                                                     depths.data_ptr(), cv.data_ptr(), sfcv.data_ptr(), B, F, D, H, W,
-                                                     float(self.alpha), cw, ws.data_ptr(), ws_bytes, stream),
-                           "mr_cost_volume_fwd_ws")
-            else:
-                _lib.check(lib.mr_cost_volume_fwd(keyframe.data_ptr(), _lib.ptr_array(frames), proj.data_ptr(),
-                                                  depths.data_ptr(), cv.data_ptr(), sfcv.data_ptr(), B, F, D, H, W,
-                                                  float(self.alpha), cw, stream), "mr_cost_volume_fwd")
+            fwd = lib.mr_cost_volume_fwd if self.tma_windows else lib.mr_cost_volume_fwd_gather
+            _lib.check(fwd(keyframe.data_ptr(), _lib.ptr_array(frames), proj.data_ptr(), depths.data_ptr(), cv.data_ptr(),
+                           sfcv.data_ptr(), B, F, D, H, W, float(self.alpha), cw, stream), "mr_cost_volume_fwd")
         data_dict["cost_volume"] = cv
         data_dict["single_frame_cvs"] = [sfcv[f] for f in range(F)]
         # host-side issue time (the reference's number includes its device work only because it synchronises implicitly)

@@ -1,25 +1,35 @@
-// Fused plane-sweep cost volume for sm_100a (B200).
+// Fused plane-sweep cost volume for sm_100a (B200), second generation: TMA-staged source windows.
 //
 // Replaces CostVolumeModule.forward (reference: model/monorec/monorec_model.py:150-280) together with
 // Backprojection / point_projection (model/layers.py:43-71), F.grid_sample x2, SSIM (layers.py:119-137), the
 // conv3d patch cost (:246-248) and the view weighting / fusion (:257-269).  Closed form: SURVEY.md Appendix C.
 //
-// Work decomposition ("warp-march"):
-//   CTA        = one keyframe tile of 60 x TH output pixels (64 x (TH+4) with the 2-px stencil halo), all D planes,
-//                all F source frames.  grid = (ceil(W/60), ceil(H/TH), B).
-//   warp       = one depth plane at a time (planes d = warp, warp+NW, ...).  The warp marches down the tile's rows:
-//                stage 1 (lane = column):  homography of the row's 64 pixels, 12 bilinear taps straight from the
-//                                          L1/L2-resident source frame, warped row -> per-warp smem row buffer;
-//                stage 2 (lane = 2 columns): 3x3 box sums of X, X^2, XY per channel as horizontal sums in registers
-//                                          and a rolling vertical sum, SSIM error, channel weighting, second 3x3
-//                                          box (horizontal neighbours by shuffle, vertical rolling) -> sad[d][row][col].
-//   CTA phase 2 (thread = pixel): min_d / sum_d exp(..) view weight, single-frame volume written to HBM once,
-//                weights kept in smem; after the last frame the fused volume is formed from the L2-hot single-frame
-//                volumes this thread wrote itself (no intermediate tensor, each output element written once).
-// Keyframe-only terms (mu_y, sigma_y + C2) are hoisted into a smem table per tile; pixels whose reprojection leaves
-// the source for any plane (valid_f = 0) are found by a projection-only pre-pass and whole row ranges / frames of the
-// tile are skipped.
+// Work decomposition:
+//   CTA   = one keyframe tile of 60 x TH output pixels (64 x (TH+4) with the 2-px stencil halo), all D planes, all F
+//           source frames.  grid = (ceil(W/60), ceil(H/TH), B).
+//   plan  = per tile and source frame the D planes are cut into groups of consecutive planes whose source footprints
+//           (projective image of the tile rectangle: extremes at its 4 corners) share one window of kPitch x kWinRows
+//           pixels.  A window is the [3][rows][kPitch] fp32 copy of that frame region, brought into shared memory by
+//           TMA boxes {kPitch, 8, 1} straight from the NCHW frame (cp.async.bulk.tensor, mbarrier complete_tx, kBuf
+//           buffers in flight); out-of-image box parts are zero-filled by the TMA unit, which is exactly
+//           F.grid_sample(padding_mode="zeros") once integer tap coordinates are clamped to the 2-px zero ring.
+//   unit  = (frame, plane).  Warps claim units from a shared counter (units of one window are consecutive), wait for
+//           the window's mbarrier, and march down the tile rows:
+//             stage 1 (lane = columns l, l+32): homography, floor by magic-number rounding, 12 bilinear taps per
+//                      sample as conflict-free LDS from the window (immediate offsets), warped row -> smem row buffer;
+//             stage 2 (lane = columns 2l, 2l+1): 3x3 box sums of X, X^2, XY (horizontal in registers, vertical rolling),
+//                      SSIM in 81x-scaled form, channel weights, second 3x3 box -> 1 - 2 sad streamed to HBM.
+//           Stage 1 of row t+1 and stage 2 of row t are issued together (double-buffered row buffer, one __syncwarp
+//           per row).  The last warp to finish a window's units re-arms the buffer with the window after next.
+//           Units whose footprint does not fit a window (strong zoom), groups of fewer than kMinGroup planes and
+//           launches whose frames TMA cannot address (W % 4 != 0, unaligned base) gather from global memory instead.
+//   CTA phase 2 (thread = pixel): view weight from max_d / sum_d exp(..), zeroing of invalid pixels, fusion over
+//           frames from the L2-hot single-frame volumes.
+// Keyframe-only terms (9 mu_y, 81 (sigma_y + C2)) are hoisted into a smem table per tile; pixels whose reprojection leaves
+// the source for any plane (valid_f = 0) are found by a projection pre-pass over the two extreme planes (the samples of
+// one pixel lie on a line, monotone in depth, so the extremes decide) and whole row ranges / frames of a tile are skipped.
 #include "mr_common.cuh"
+#include <cuda.h>
 #include <cstdint>
 #include <type_traits>
 
@@ -28,17 +38,43 @@ namespace {
 constexpr int kTileCols = 64;   // buffer columns per tile row (output columns + 2-px halo each side)
 constexpr int kOutCols = 60;    // output columns per tile
 constexpr int kRowStride = 68;  // floats per smem image row: column b lives at index b+1 (so [2l-1, 2l+2] is 8B aligned)
-#ifndef MR_CV_THREADS
-#define MR_CV_THREADS 512
+#ifndef MR_CV_WARPS
+#define MR_CV_WARPS 16
 #endif
-constexpr int kThreads = MR_CV_THREADS;
 #ifndef MR_CV_MINBLOCKS
-#define MR_CV_MINBLOCKS 1      // resident CTAs per SM the register allocator must leave room for
+#define MR_CV_MINBLOCKS 1       // resident CTAs per SM the register allocator must leave room for
 #endif
+#ifndef MR_CV_NBUF
+#define MR_CV_NBUF 2            // source windows in flight per CTA
+#endif
+#ifndef MR_CV_WIN_ROWS
+#define MR_CV_WIN_ROWS 40       // rows per window (multiple of 8)
+#endif
+#ifndef MR_CV_MIN_GROUP
+#define MR_CV_MIN_GROUP 3       // plane groups smaller than this gather from global memory
+#endif
+#ifndef MR_CV_TILE_ROWS
+#define MR_CV_TILE_ROWS 16
+#endif
+#ifndef MR_CV_SKIP
+#define MR_CV_SKIP 0            // timing experiments only: 1 = no march, 2 = no per-pixel phase, 3 = march without stage 2, 4 = without stage 1
+#endif
+constexpr int kWarps = MR_CV_WARPS;
+constexpr int kThreads = kWarps * 32;
+constexpr int kBuf = MR_CV_NBUF;
+constexpr int kPitch = 128;                       // pixels per window row (512 bytes)
+constexpr int kWinRows = MR_CV_WIN_ROWS;
+constexpr int kChanStride = kWinRows * kPitch;    // floats between the channel planes of a window
+constexpr int kWinFloats = 3 * kChanStride;
+constexpr int kBoxRows = 8;                       // rows per TMA box
+constexpr int kMinGroup = MR_CV_MIN_GROUP;
+static_assert(kWinRows % kBoxRows == 0, "window rows must be a multiple of the TMA box height");
 
-constexpr int kWarps = kThreads / 32;
 constexpr float kC1 = 0.01f * 0.01f;  // layers.py:116
 constexpr float kC2 = 0.03f * 0.03f;  // layers.py:117
+constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
+constexpr int kMagicBits = 0x4B400000;
+constexpr int kChunk = 32;                 // planes the per-pixel phase keeps in registers at once
 
 struct CvArgs {
     const float* key;                    // [B,3,H,W]
@@ -47,26 +83,49 @@ struct CvArgs {
     const float* depths;                 // [D]
     float* cv;                           // [B,D,H,W]
     float* sfcv;                         // [F,B,D,H,W]
-    const float4* packed;                // [F,B,H,W] (r,g,b,0) copies of the source frames, or nullptr (planar gather)
     int B, F, D, H, W, TH, b0;
+    int use_tma;                         // 0: every unit gathers from global memory
     float alpha, inv_dm1;
     float cw0, cw1, cw2;                 // channel weights / 9
 };
 
-struct SmemLayout {
-    int ytile, cst, xbuf, pjs, zs, vmask, rowrng, total;  // byte offsets
+struct CvMaps {
+    CUtensorMap m[MR_MAX_FRAMES];        // frame f as a (W, H, 3B) fp32 tensor, box {kPitch, kBoxRows, 1}, zero fill
 };
 
-__host__ __device__ inline SmemLayout make_layout(int D, int TH, int F) {
+struct GroupInfo {                       // one window (a run of consecutive planes of one frame)
+    short wx0, wy0;                      // image coordinates of the window origin (may be negative: zero ring)
+    short nrows;                         // rows actually loaded (multiple of kBoxRows)
+    short f;
+    short count;                         // planes in the group
+    short seq;                           // running number of the window inside the tile (buffer = seq % kBuf)
+    short pad0, pad1;
+};
+
+struct SmemLayout {
+    int win, ytile, cst, xbuf, pjs, zs, vmask, rowrng, bbox, gid, uflag, ginfo, seq2g, nwin, bars, ctr, total;  // byte offsets
+};
+
+__host__ __device__ inline SmemLayout make_layout(int D, int TH, int F, int use_tma) {
     SmemLayout L;
     int off = 0;
-    L.ytile = off; off += 3 * (TH + 4) * kRowStride * 4;
-    L.cst = off;   off += 3 * (TH + 2) * kTileCols * 8;
-    L.xbuf = off;  off += kWarps * 3 * kRowStride * 4;
-    L.pjs = off;   off += F * 12 * 4;
-    L.zs = off;    off += ((D + 3) / 4) * 16;
-    L.vmask = off; off += F * TH * kTileCols;
-    L.rowrng = off; off += F * 2 * 4;
+    auto take = [&](int bytes, int align) { off = (off + align - 1) / align * align; int o = off; off += bytes; return o; };
+    L.win = take(use_tma ? kBuf * kWinFloats * 4 : 0, 128);
+    L.ytile = take(3 * (TH + 4) * kRowStride * 4, 16);
+    L.cst = take(3 * (TH + 2) * kTileCols * 8, 16);
+    L.xbuf = take(kWarps * 2 * 3 * kRowStride * 4, 16);
+    L.pjs = take(F * 12 * 4, 16);
+    L.zs = take(((D + 3) / 4) * 16, 16);
+    L.vmask = take(F * TH * kTileCols, 16);
+    L.rowrng = take(F * 2 * 4, 16);
+    L.bbox = take(F * D * 8, 8);
+    L.gid = take(F * D * 2, 4);
+    L.uflag = take(F * D, 4);
+    L.ginfo = take(F * D * (int)sizeof(GroupInfo), 16);
+    L.seq2g = take(F * D * 2, 4);
+    L.nwin = take(MR_MAX_FRAMES * 4, 4);
+    L.bars = take(kBuf * 8, 8);
+    L.ctr = take((2 + 2 * kBuf) * 4, 4);
     L.total = off;
     return L;
 }
@@ -104,34 +163,77 @@ __device__ __forceinline__ void st_hint_f1(float* ptr, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(pol) : "memory");
 }
 
-
-constexpr int kChunk = 32;                 // planes the per-pixel phase keeps in registers at once
-constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
-constexpr int kMagicBits = 0x4B400000;
-
-// SSIM numerator / denominator for a pair of columns (layers.py:123-134 through 3x3 box sums; mu_y, sigma_y + C2 hoisted)
-__device__ __forceinline__ void ssim_nd(float2 s1, float2 sxx, float2 sxy, float2 mu_y, float2 sy2, float2& n, float2& d) {
-    const float2 k9 = bc2(1.0f / 9.0f);
-    float2 mu_x = mul2(s1, k9);
-    float2 mxy = mul2(mu_x, mu_y);
-    float2 mxx = mul2(mu_x, mu_x);
-    float2 sig_xy = fma2(sxy, k9, neg2(mxy));
-    float2 sig_x = fma2(sxx, k9, neg2(mxx));
-    n = mul2(fma2(bc2(2.0f), mxy, bc2(kC1)), fma2(bc2(2.0f), sig_xy, bc2(kC2)));
-    d = mul2(add2(mxx, fma2(mu_y, mu_y, bc2(kC1))), add2(sig_x, sy2));
+// ---- mbarrier / TMA wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a window that never arrives (a bug, not a load condition) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// ---- explicit shared-memory accesses (32-bit shared addresses, immediate offsets) ---------------------------------------
+// volatile: never hoisted over the mbarrier wait / __syncwarp that orders them; ptxas still schedules them freely
+template <int OFF>
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory");
+}
+
+constexpr int kXbBytes = 3 * kRowStride * 4;      // one warped-row buffer (3 channels)
+constexpr int kYRowBytes = 3 * kRowStride * 4;    // keyframe tile: [row][channel][kRowStride]
+constexpr int kCRowBytes = 3 * (kTileCols / 2) * 16;  // hoisted table: [e-row][channel][32 column pairs] float4
 
 // ---- stage 1 of the march: homography of one tile row (pair = columns lane, lane + 32) and its 24 bilinear taps -------
 struct Stage1Ctx {
-    float2 pzx, pzy, pzz;             // per-lane column part of the projection (already times the plane depth)
+    float2 pzx, pzy, pzz;                // per-lane column part of the projection (already times the plane depth)
     float rax, rbx, ray, rby, raz, rbz;  // per-row part: c = pz(u) + ra * v + rb
-    const float* img;                 // source frame of this batch element, [3][H][W]
-    const float4* img4;               // the same frame as [H][W] (r,g,b,0) pixels (packed gather) or nullptr
-    int W, H, planei, v0, lane;
-    float sx_lo, sx_hi, sy_lo, sy_hi; // == grid clamp(-2, 2), monorec_model.py:208
+    uint32_t kaddr;                      // window modes: shared address of the window minus the unit's constant (see march)
+    const float* img;                    // global mode: source frame of this batch element, [3][H][W]
+    int W, H, planei;
+    float sx_lo, sx_hi, sy_lo, sy_hi;    // == grid clamp(-2, 2) + 0.5, monorec_model.py:208
 };
 
-__device__ __forceinline__ void setup_stage1(Stage1Ctx& c, const float* m, const float* img, float z, float2 fu2) {
+__device__ __forceinline__ void setup_stage1(Stage1Ctx& c, const float* m, float z, float2 fu2) {
     // projection c = M [u v 1]^T z + p split into a per-lane column part and a per-row part
     c.pzx = mul2(mul2(bc2(m[0]), fu2), bc2(z));
     c.pzy = mul2(mul2(bc2(m[4]), fu2), bc2(z));
@@ -139,107 +241,140 @@ __device__ __forceinline__ void setup_stage1(Stage1Ctx& c, const float* m, const
     c.rax = m[1] * z; c.rbx = fmaf(m[2], z, m[3]);
     c.ray = m[5] * z; c.rby = fmaf(m[6], z, m[7]);
     c.raz = m[9] * z; c.rbz = fmaf(m[10], z, m[11]);
-    c.img = img;
 }
 
-template <bool PACKED>
-__device__ __forceinline__ void warp_row(const Stage1Ctx& c, const int r, float* __restrict__ xrow) {
-    const int W = c.W, H = c.H;
-    const float fv = (float)(c.v0 + r);
+struct Taps {                            // the 24 taps and 4 weight pairs of one row step (two samples per lane)
+    float a[3][4], b[3][4];              // [channel][nw, ne, sw, se] of the sample at column lane / lane + 32
+    float2 w00, w01, w10, w11;
+};
+
+// MODE 0: taps from the window, every sample of the unit strictly inside the image (decided by the plan): no clamps
+// MODE 1: taps from the window, coordinates clamped to the 2-px zero ring (== zero padding of F.grid_sample)
+// MODE 2: taps from global memory with per-tap zero padding
+template <int MODE>
+__device__ __forceinline__ void warp_row_issue(const Stage1Ctx& c, const float fv, Taps& t) {
     const float rcx = fmaf(c.rax, fv, c.rbx), rcy = fmaf(c.ray, fv, c.rby), rcz = fmaf(c.raz, fv, c.rbz);
     const float2 cx = add2(c.pzx, bc2(rcx)), cy = add2(c.pzy, bc2(rcy)), cz = add2(c.pzz, bc2(rcz));
     const float2 inv = make_float2(fast_rcp(cz.x), fast_rcp(cz.y));
-    const float2 ux = mul2(cx, inv), uy = mul2(cy, inv);
-    // floor by magic-number rounding: rn(s - 0.5) differs from floor(s) only for integral s, where the interpolated value
-    // is the same (weight 1 on the tap both conventions share)
-    const float2 tx = add2(ux, bc2(kMagic - 1.0f)), ty = add2(uy, bc2(kMagic - 1.0f));
-    const int x0a = __float_as_int(tx.x) - kMagicBits, x0b = __float_as_int(tx.y) - kMagicBits;
-    const int y0a = __float_as_int(ty.x) - kMagicBits, y0b = __float_as_int(ty.y) - kMagicBits;
-    const bool inb = ((unsigned)x0a <= (unsigned)(W - 2)) && ((unsigned)x0b <= (unsigned)(W - 2)) &&
-                     ((unsigned)y0a <= (unsigned)(H - 2)) && ((unsigned)y0b <= (unsigned)(H - 2));
-    float2 w00, w01, w10, w11;
-    int oa, ob, dxa, dxb, dya, dyb;
-    if (__all_sync(0xffffffffu, inb)) {
-        // fast path: all 4 taps of every lane are inside the image
+    float2 ux = mul2(cx, inv), uy = mul2(cy, inv);   // sample position + 0.5
+    if (MODE <= 1) {
+        if (MODE == 1) {   // == .clamp(-2, 2) of the normalised grid (monorec_model.py:208); also maps NaN to the low bound
+            ux.x = fminf(fmaxf(ux.x, c.sx_lo), c.sx_hi); ux.y = fminf(fmaxf(ux.y, c.sx_lo), c.sx_hi);
+            uy.x = fminf(fmaxf(uy.x, c.sy_lo), c.sy_hi); uy.y = fminf(fmaxf(uy.y, c.sy_lo), c.sy_hi);
+        }
+        // floor by magic-number rounding: rn(s - 0.5) differs from floor(s) only for integral s, where the interpolated value
+        // is the same (weight 1 on the tap both conventions share)
+        const float2 tx = add2(ux, bc2(kMagic - 1.0f)), ty = add2(uy, bc2(kMagic - 1.0f));
         const float2 x0f = add2(tx, bc2(-kMagic)), y0f = add2(ty, bc2(-kMagic));
         const float2 wx1 = add2(add2(ux, bc2(-0.5f)), neg2(x0f)), wy1 = add2(add2(uy, bc2(-0.5f)), neg2(y0f));
         const float2 wx0 = add2(bc2(1.0f), neg2(wx1)), wy0 = add2(bc2(1.0f), neg2(wy1));
-        w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
-        oa = y0a * W + x0a; ob = y0b * W + x0b;
-        dxa = dxb = 1; dya = dyb = W;
-    } else {
-        // border path: per-tap zero padding exactly like F.grid_sample(padding_mode="zeros"): clamp the tap address, zero
-        // the weight of every tap that falls outside the image
-        float wx0s[2], wx1s[2], wy0s[2], wy1s[2];
-        int os[2], dxs[2], dys[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            float sxk = (k ? ux.y : ux.x) - 0.5f, syk = (k ? uy.y : uy.x) - 0.5f;
-            sxk = fminf(fmaxf(sxk, c.sx_lo), c.sx_hi);
-            syk = fminf(fmaxf(syk, c.sy_lo), c.sy_hi);
-            const float x0f = floorf(sxk), y0f = floorf(syk);
-            float wx1 = sxk - x0f, wy1 = syk - y0f;
-            float wx0 = (x0f + 1.0f) - sxk, wy0 = (y0f + 1.0f) - syk;
-            const int x0 = (int)x0f, y0 = (int)y0f;
-            if ((unsigned)x0 >= (unsigned)W) wx0 = 0.f;
-            if ((unsigned)(x0 + 1) >= (unsigned)W) wx1 = 0.f;
-            if ((unsigned)y0 >= (unsigned)H) wy0 = 0.f;
-            if ((unsigned)(y0 + 1) >= (unsigned)H) wy1 = 0.f;
-            const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
-            const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
-            wx0s[k] = wx0; wx1s[k] = wx1; wy0s[k] = wy0; wy1s[k] = wy1;
-            os[k] = ya * W + xa; dxs[k] = xb - xa; dys[k] = (yb - ya) * W;
+        t.w00 = mul2(wx0, wy0); t.w01 = mul2(wx1, wy0); t.w10 = mul2(wx0, wy1); t.w11 = mul2(wx1, wy1);
+        uint32_t aa, ab;
+        if (MODE == 0) {
+            // address = window + 4 ((y0 - wy0) kPitch + x0 - wx0) with y0 = bits(ty) - kMagicBits: every constant is in kaddr
+            aa = ((((uint32_t)__float_as_int(ty.x) << 7) + (uint32_t)__float_as_int(tx.x)) << 2) + c.kaddr;
+            ab = ((((uint32_t)__float_as_int(ty.y) << 7) + (uint32_t)__float_as_int(tx.y)) << 2) + c.kaddr;
+        } else {
+            // integer tap origin clamped to [-2, W] x [-2, H]: taps of the ring [-2,-1] / [W, W+1] are zero-filled by TMA
+            const int xa = min(max(__float_as_int(tx.x) - kMagicBits, -2), c.W);
+            const int xb = min(max(__float_as_int(tx.y) - kMagicBits, -2), c.W);
+            const int ya = min(max(__float_as_int(ty.x) - kMagicBits, -2), c.H);
+            const int yb = min(max(__float_as_int(ty.y) - kMagicBits, -2), c.H);
+            aa = ((((uint32_t)ya << 7) + (uint32_t)xa) << 2) + c.kaddr;
+            ab = ((((uint32_t)yb << 7) + (uint32_t)xb) << 2) + c.kaddr;
         }
-        const float2 wx0 = make_float2(wx0s[0], wx0s[1]), wx1 = make_float2(wx1s[0], wx1s[1]);
-        const float2 wy0 = make_float2(wy0s[0], wy0s[1]), wy1 = make_float2(wy1s[0], wy1s[1]);
-        w00 = mul2(wx0, wy0); w01 = mul2(wx1, wy0); w10 = mul2(wx0, wy1); w11 = mul2(wx1, wy1);
-        oa = os[0]; ob = os[1]; dxa = dxs[0]; dxb = dxs[1]; dya = dys[0]; dyb = dys[1];
-    }
-    if (PACKED) {
-        // one 16-byte load per tap: 8 requests per row step instead of 24 (stage 1 is bound by L1/LSU requests)
-        const float4* qa = c.img4 + oa;
-        const float4* qb = c.img4 + ob;
-        const float4 a00 = __ldg(qa), a01 = __ldg(qa + dxa), a10 = __ldg(qa + dya), a11 = __ldg(qa + dya + dxa);
-        const float4 b00 = __ldg(qb), b01 = __ldg(qb + dxb), b10 = __ldg(qb + dyb), b11 = __ldg(qb + dyb + dxb);
-        float2 v0 = fma2(make_float2(a00.x, b00.x), w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
-        float2 v1 = fma2(make_float2(a00.y, b00.y), w00, bc2(0.5f));
-        float2 v2 = fma2(make_float2(a00.z, b00.z), w00, bc2(0.5f));
-        v0 = fma2(make_float2(a01.x, b01.x), w01, v0); v1 = fma2(make_float2(a01.y, b01.y), w01, v1); v2 = fma2(make_float2(a01.z, b01.z), w01, v2);
-        v0 = fma2(make_float2(a10.x, b10.x), w10, v0); v1 = fma2(make_float2(a10.y, b10.y), w10, v1); v2 = fma2(make_float2(a10.z, b10.z), w10, v2);
-        v0 = fma2(make_float2(a11.x, b11.x), w11, v0); v1 = fma2(make_float2(a11.y, b11.y), w11, v1); v2 = fma2(make_float2(a11.z, b11.z), w11, v2);
-        xrow[c.lane + 1] = v0.x;                  xrow[c.lane + 33] = v0.y;
-        xrow[kRowStride + c.lane + 1] = v1.x;     xrow[kRowStride + c.lane + 33] = v1.y;
-        xrow[2 * kRowStride + c.lane + 1] = v2.x; xrow[2 * kRowStride + c.lane + 33] = v2.y;
+        static_assert(kPitch == 128, "the tap address uses a shift by 7");
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            // (ch is a compile-time constant after unrolling: the offsets are immediates)
+            if (ch == 0) {
+                t.a[0][0] = lds32<0>(aa); t.a[0][1] = lds32<4>(aa); t.a[0][2] = lds32<kPitch * 4>(aa); t.a[0][3] = lds32<kPitch * 4 + 4>(aa);
+                t.b[0][0] = lds32<0>(ab); t.b[0][1] = lds32<4>(ab); t.b[0][2] = lds32<kPitch * 4>(ab); t.b[0][3] = lds32<kPitch * 4 + 4>(ab);
+            } else if (ch == 1) {
+                constexpr int o = kChanStride * 4;
+                t.a[1][0] = lds32<o>(aa); t.a[1][1] = lds32<o + 4>(aa); t.a[1][2] = lds32<o + kPitch * 4>(aa); t.a[1][3] = lds32<o + kPitch * 4 + 4>(aa);
+                t.b[1][0] = lds32<o>(ab); t.b[1][1] = lds32<o + 4>(ab); t.b[1][2] = lds32<o + kPitch * 4>(ab); t.b[1][3] = lds32<o + kPitch * 4 + 4>(ab);
+            } else {
+                constexpr int o = 2 * kChanStride * 4;
+                t.a[2][0] = lds32<o>(aa); t.a[2][1] = lds32<o + 4>(aa); t.a[2][2] = lds32<o + kPitch * 4>(aa); t.a[2][3] = lds32<o + kPitch * 4 + 4>(aa);
+                t.b[2][0] = lds32<o>(ab); t.b[2][1] = lds32<o + 4>(ab); t.b[2][2] = lds32<o + kPitch * 4>(ab); t.b[2][3] = lds32<o + kPitch * 4 + 4>(ab);
+            }
+        }
     } else {
+        const int W = c.W, H = c.H;
+        const float2 tx = add2(ux, bc2(kMagic - 1.0f)), ty = add2(uy, bc2(kMagic - 1.0f));
+        const int x0a = __float_as_int(tx.x) - kMagicBits, x0b = __float_as_int(tx.y) - kMagicBits;
+        const int y0a = __float_as_int(ty.x) - kMagicBits, y0b = __float_as_int(ty.y) - kMagicBits;
+        const bool inb = ((unsigned)x0a <= (unsigned)(W - 2)) && ((unsigned)x0b <= (unsigned)(W - 2)) &&
+                         ((unsigned)y0a <= (unsigned)(H - 2)) && ((unsigned)y0b <= (unsigned)(H - 2));
+        int oa, ob, dxa, dxb, dya, dyb;
+        if (__all_sync(0xffffffffu, inb)) {
+            const float2 x0f = add2(tx, bc2(-kMagic)), y0f = add2(ty, bc2(-kMagic));
+            const float2 wx1 = add2(add2(ux, bc2(-0.5f)), neg2(x0f)), wy1 = add2(add2(uy, bc2(-0.5f)), neg2(y0f));
+            const float2 wx0 = add2(bc2(1.0f), neg2(wx1)), wy0 = add2(bc2(1.0f), neg2(wy1));
+            t.w00 = mul2(wx0, wy0); t.w01 = mul2(wx1, wy0); t.w10 = mul2(wx0, wy1); t.w11 = mul2(wx1, wy1);
+            oa = y0a * W + x0a; ob = y0b * W + x0b;
+            dxa = dxb = 1; dya = dyb = W;
+        } else {
+            // border path: per-tap zero padding exactly like F.grid_sample(padding_mode="zeros"): clamp the tap address, zero
+            // the weight of every tap that falls outside the image
+            float wx0s[2], wx1s[2], wy0s[2], wy1s[2];
+            int os[2], dxs[2], dys[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                float sxk = (k ? ux.y : ux.x), syk = (k ? uy.y : uy.x);
+                sxk = fminf(fmaxf(sxk, c.sx_lo), c.sx_hi) - 0.5f;
+                syk = fminf(fmaxf(syk, c.sy_lo), c.sy_hi) - 0.5f;
+                const float x0f = floorf(sxk), y0f = floorf(syk);
+                float wx1 = sxk - x0f, wy1 = syk - y0f;
+                float wx0 = (x0f + 1.0f) - sxk, wy0 = (y0f + 1.0f) - syk;
+                const int x0 = (int)x0f, y0 = (int)y0f;
+                if ((unsigned)x0 >= (unsigned)W) wx0 = 0.f;
+                if ((unsigned)(x0 + 1) >= (unsigned)W) wx1 = 0.f;
+                if ((unsigned)y0 >= (unsigned)H) wy0 = 0.f;
+                if ((unsigned)(y0 + 1) >= (unsigned)H) wy1 = 0.f;
+                const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+                const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
+                wx0s[k] = wx0; wx1s[k] = wx1; wy0s[k] = wy0; wy1s[k] = wy1;
+                os[k] = ya * W + xa; dxs[k] = xb - xa; dys[k] = (yb - ya) * W;
+            }
+            const float2 wx0 = make_float2(wx0s[0], wx0s[1]), wx1 = make_float2(wx1s[0], wx1s[1]);
+            const float2 wy0 = make_float2(wy0s[0], wy0s[1]), wy1 = make_float2(wy1s[0], wy1s[1]);
+            t.w00 = mul2(wx0, wy0); t.w01 = mul2(wx1, wy0); t.w10 = mul2(wx0, wy1); t.w11 = mul2(wx1, wy1);
+            oa = os[0]; ob = os[1]; dxa = dxs[0]; dxb = dxs[1]; dya = dys[0]; dyb = dys[1];
+        }
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
             const float* pa0 = c.img + (oa + ch * c.planei);
             const float* pb0 = c.img + (ob + ch * c.planei);
-            const float* pa1 = pa0 + dya;
-            const float* pb1 = pb0 + dyb;
-            const float2 i00 = make_float2(__ldg(pa0), __ldg(pb0));
-            const float2 i01 = make_float2(__ldg(pa0 + dxa), __ldg(pb0 + dxb));
-            const float2 i10 = make_float2(__ldg(pa1), __ldg(pb1));
-            const float2 i11 = make_float2(__ldg(pa1 + dxa), __ldg(pb1 + dxb));
-            float2 val = fma2(i00, w00, bc2(0.5f));   // + 0.5: monorec_model.py:231
-            val = fma2(i01, w01, val);
-            val = fma2(i10, w10, val);
-            val = fma2(i11, w11, val);
-            xrow[ch * kRowStride + c.lane + 1] = val.x;
-            xrow[ch * kRowStride + c.lane + 33] = val.y;
+            t.a[ch][0] = __ldg(pa0); t.a[ch][1] = __ldg(pa0 + dxa); t.a[ch][2] = __ldg(pa0 + dya); t.a[ch][3] = __ldg(pa0 + dya + dxa);
+            t.b[ch][0] = __ldg(pb0); t.b[ch][1] = __ldg(pb0 + dxb); t.b[ch][2] = __ldg(pb0 + dyb); t.b[ch][3] = __ldg(pb0 + dyb + dxb);
         }
     }
 }
 
+// interpolation (same order as grid_sample: nw, ne, sw, se; + 0.5: monorec_model.py:231) and the warped row -> row buffer
+// xw = shared address of this lane's first column in the row buffer to fill
+__device__ __forceinline__ void warp_row_finish(const Taps& t, const uint32_t xw) {
+    float va[3], vb[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        float a = fmaf(t.a[ch][0], t.w00.x, 0.5f), b = fmaf(t.b[ch][0], t.w00.y, 0.5f);
+        a = fmaf(t.a[ch][1], t.w01.x, a); b = fmaf(t.b[ch][1], t.w01.y, b);
+        a = fmaf(t.a[ch][2], t.w10.x, a); b = fmaf(t.b[ch][2], t.w10.y, b);
+        a = fmaf(t.a[ch][3], t.w11.x, a); b = fmaf(t.b[ch][3], t.w11.y, b);
+        va[ch] = a; vb[ch] = b;
+    }
+    sts32<0>(xw, va[0]);                  sts32<128>(xw, vb[0]);
+    sts32<kRowStride * 4>(xw, va[1]);     sts32<kRowStride * 4 + 128>(xw, vb[1]);
+    sts32<2 * kRowStride * 4>(xw, va[2]); sts32<2 * kRowStride * 4 + 128>(xw, vb[2]);
+}
+
 // ---- stage 2 of the march: SSIM + patch cost of one row; lane owns buffer columns 2l, 2l+1 (a pair) ---------------------
 struct Stage2Ctx {
-    const float* ys_l;       // keyframe tile (+0.5), this lane's columns
-    const float4* cs_l;      // hoisted (mu_y, sigma_y + C2) table, this lane's column pair
-    int ych, cch;            // channel strides of the two tables
     float2 cw0, cw1, cw2;    // channel weights / 9
-    float* out_d;            // single-frame volume plane, tile row 0, this lane's columns
-    int W, rows_left;        // rows_left = H - v0
-    bool st_pair, st0, st1;
+    int pairflag;            // 1: both columns of this lane are output pixels and W is even (one 8-byte store)
+    bool st0, st1;
     uint64_t pol_keep;
 };
 
@@ -257,79 +392,147 @@ struct Stage2State {
     }
 };
 
-// STAGE selects how far the two cascaded 3x3 windows are filled: 0 = rows 0,1 of a unit (only the horizontal sums are
-// recorded), 1 = rows 2,3 (SSIM error row available, patch window not yet), 2 = steady state (a cost row is stored).
-// Making it a template parameter keeps the steady-state step one branch-free block, so the three channels' dependency
-// chains are scheduled against each other.
-template <int P, int STAGE>
-__device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, const int r, const float* __restrict__ xs_l) {
+// One row step: horizontal sums of the new warped row, SSIM error of the row above it (windows complete from the third
+// row of a unit on; earlier rows produce finite throw-away values from the zeroed state: 9 sxx >= s^2 for partial
+// windows too), patch cost of the row above that.  `store` is warp-uniform (false for the first four rows of a unit).
+//   xr: shared address of the warped row (this lane's columns 2l-1..2l+2); yr: keyframe tile row (+0.5), same columns;
+//   cr: hoisted (Y, Y, Sg, Sg) table row of the SSIM row; out: single-frame volume, output row of this step.
+template <int P>
+__device__ __forceinline__ void ssim_row(Stage2State& st, const Stage2Ctx& c, const uint32_t xr, const uint32_t yr,
+                                         const uint32_t cr, float* out, const bool store) {
     constexpr int P1 = (P + 1) % 3, P2 = (P + 2) % 3;
-    const float* yrow = c.ys_l + (r + 2) * kRowStride;
+    float2 xl[3], xrr[3], yl[3], yrr[3];
+    float4 k4[3];
+    xl[0] = lds64<0>(xr);                  xrr[0] = lds64<8>(xr);
+    xl[1] = lds64<kRowStride * 4>(xr);     xrr[1] = lds64<kRowStride * 4 + 8>(xr);
+    xl[2] = lds64<2 * kRowStride * 4>(xr); xrr[2] = lds64<2 * kRowStride * 4 + 8>(xr);
+    yl[0] = lds64<0>(yr);                  yrr[0] = lds64<8>(yr);
+    yl[1] = lds64<kRowStride * 4>(yr);     yrr[1] = lds64<kRowStride * 4 + 8>(yr);
+    yl[2] = lds64<2 * kRowStride * 4>(yr); yrr[2] = lds64<2 * kRowStride * 4 + 8>(yr);
+    k4[0] = lds128<0>(cr); k4[1] = lds128<512>(cr); k4[2] = lds128<1024>(cr);
     float2 h1[3], hx[3], hy[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-        const float2 xl = *reinterpret_cast<const float2*>(xs_l + ch * kRowStride);      // cols 2l-1, 2l
-        const float2 xr = *reinterpret_cast<const float2*>(xs_l + ch * kRowStride + 2);  // cols 2l+1, 2l+2
-        const float2 yl = *reinterpret_cast<const float2*>(yrow + ch * c.ych);
-        const float2 yr = *reinterpret_cast<const float2*>(yrow + ch * c.ych + 2);
-        const float2 xxl = mul2(xl, xl), xxr = mul2(xr, xr), xyl = mul2(xl, yl), xyr = mul2(xr, yr);
-        const float m1 = xl.y + xr.x, mx = xxl.y + xxr.x, my = xyl.y + xyr.x;
-        h1[ch] = make_float2(xl.x + m1, m1 + xr.y);
+        const float2 xxl = mul2(xl[ch], xl[ch]), xxr = mul2(xrr[ch], xrr[ch]), xyl = mul2(xl[ch], yl[ch]), xyr = mul2(xrr[ch], yrr[ch]);
+        const float m1 = xl[ch].y + xrr[ch].x, mx = xxl.y + xxr.x, my = xyl.y + xyr.x;
+        h1[ch] = make_float2(xl[ch].x + m1, m1 + xrr[ch].y);
         hx[ch] = make_float2(xxl.x + mx, mx + xxr.y);
         hy[ch] = make_float2(xyl.x + my, my + xyr.y);
     }
-    if (STAGE >= 1) {
-        float2 nn[3], dd[3];
+    float2 e[3];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float4 k4 = c.cs_l[ch * c.cch + r * (kTileCols / 2)];
-            ssim_nd(add2(add2(st.hs1[P1][ch], st.hs1[P2][ch]), h1[ch]), add2(add2(st.hsx[P1][ch], st.hsx[P2][ch]), hx[ch]),
-                    add2(add2(st.hsy[P1][ch], st.hsy[P2][ch]), hy[ch]), make_float2(k4.x, k4.y), make_float2(k4.z, k4.w),
-                    nn[ch], dd[ch]);
-        }
-        const float2 q0 = mul2(nn[0], make_float2(fast_rcp(dd[0].x), fast_rcp(dd[0].y)));
-        const float2 q1 = mul2(nn[1], make_float2(fast_rcp(dd[1].x), fast_rcp(dd[1].y)));
-        const float2 q2 = mul2(nn[2], make_float2(fast_rcp(dd[2].x), fast_rcp(dd[2].y)));
-        // clamp((1 - q) / 2, 0, 1)   (layers.py:137)
-        const float2 e0 = make_float2(__saturatef(fmaf(-0.5f, q0.x, 0.5f)), __saturatef(fmaf(-0.5f, q0.y, 0.5f)));
-        const float2 e1 = make_float2(__saturatef(fmaf(-0.5f, q1.x, 0.5f)), __saturatef(fmaf(-0.5f, q1.y, 0.5f)));
-        const float2 e2 = make_float2(__saturatef(fmaf(-0.5f, q2.x, 0.5f)), __saturatef(fmaf(-0.5f, q2.y, 0.5f)));
-        const float2 E = fma2(c.cw2, e2, fma2(c.cw1, e1, mul2(c.cw0, e0)));
-        const float eL = __shfl_up_sync(0xffffffffu, E.y, 1);
-        const float eR = __shfl_down_sync(0xffffffffu, E.x, 1);
-        const float mid = E.x + E.y;
-        const float2 hEc = make_float2(eL + mid, mid + eR);
-        if (STAGE >= 2) {
-            // single-frame volume 1 - 2 sad (monorec_model.py:251) straight to HBM; the validity mask is applied by the
-            // per-pixel phase (which zeroes invalid pixels) once all planes are known
-            const float2 sad = add2(add2(st.hE[P1], st.hE[P2]), hEc);
-            const float2 sv = fma2(bc2(-2.0f), sad, bc2(1.0f));
-            float* o = c.out_d + (size_t)(r - 2) * c.W;
-            if (r - 2 < c.rows_left) {
-                if (c.st_pair) {
-                    st_hint_f2(o, sv, c.pol_keep);
-                } else {
-                    if (c.st0) st_hint_f1(o, sv.x, c.pol_keep);
-                    if (c.st1) st_hint_f1(o + 1, sv.y, c.pol_keep);
-                }
-            }
-        }
-        st.hE[P] = hEc;
+    for (int ch = 0; ch < 3; ++ch) {
+        // SSIM with every factor scaled by 81 (layers.py:123-137 through 3x3 box sums s = sum x, sxx, sxy; Y = 9 mu_y,
+        // Sg = 81 (sigma_y + C2) hoisted):  n/d = (2 s Y + 81 C1)(2 (9 sxy - s Y) + 81 C2) / ((s^2 + Y^2 + 81 C1)(9 sxx - s^2 + Sg))
+        const float2 Y = make_float2(k4[ch].x, k4[ch].y), Sg = make_float2(k4[ch].z, k4[ch].w);
+        const float2 s = add2(add2(st.hs1[P1][ch], st.hs1[P2][ch]), h1[ch]);
+        const float2 sxx = add2(add2(st.hsx[P1][ch], st.hsx[P2][ch]), hx[ch]);
+        const float2 sxy = add2(add2(st.hsy[P1][ch], st.hsy[P2][ch]), hy[ch]);
+        const float2 p = mul2(s, Y), q = mul2(s, s);
+        const float2 n1h = add2(neg2(p), bc2(-40.5f * kC1));                 // -(N1 / 2)
+        const float2 n2 = fma2(bc2(2.0f), fma2(bc2(9.0f), sxy, neg2(p)), bc2(81.0f * kC2));
+        const float2 d1 = add2(q, fma2(Y, Y, bc2(81.0f * kC1)));
+        const float2 d2 = add2(fma2(bc2(9.0f), sxx, Sg), neg2(q));
+        const float2 num = mul2(n1h, n2), den = mul2(d1, d2);
+        // clamp((1 - n/d) / 2, 0, 1)   (layers.py:137)
+        e[ch] = make_float2(__saturatef(fmaf(num.x, fast_rcp(den.x), 0.5f)), __saturatef(fmaf(num.y, fast_rcp(den.y), 0.5f)));
     }
+    const float2 E = fma2(c.cw2, e[2], fma2(c.cw1, e[1], mul2(c.cw0, e[0])));
+    const float eL = __shfl_up_sync(0xffffffffu, E.y, 1);
+    const float eR = __shfl_down_sync(0xffffffffu, E.x, 1);
+    const float mid = E.x + E.y;
+    const float2 hEc = make_float2(eL + mid, mid + eR);
+    // single-frame volume 1 - 2 sad (monorec_model.py:251) straight to HBM; the validity mask is applied by the
+    // per-pixel phase (which zeroes invalid pixels) once all planes are known
+    const float2 sad = add2(add2(st.hE[P1], st.hE[P2]), hEc);
+    const float2 sv = fma2(bc2(-2.0f), sad, bc2(1.0f));
+    if (store) {
+        if (c.pairflag) {
+            st_hint_f2(out, sv, c.pol_keep);
+        } else {
+            if (c.st0) st_hint_f1(out, sv.x, c.pol_keep);
+            if (c.st1) st_hint_f1(out + 1, sv.y, c.pol_keep);
+        }
+    }
+    st.hE[P] = hEc;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) { st.hs1[P][ch] = h1[ch]; st.hsx[P][ch] = hx[ch]; st.hsy[P][ch] = hy[ch]; }
 }
 
-template <bool PACKED>
-__global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(const CvArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = make_layout(a.D, a.TH, a.F);
+#ifndef MR_CV_ORDER
+#define MR_CV_ORDER 0     // 0: stage 1 of row t+1 completes, then stage 2 of row t (measured faster: 1.07 vs 1.12 ms); 1: taps stay in flight across stage 2
+#endif
+
+// The march of one unit over tile rows rlo-2 .. rhi+2 (nsteps = rhi - rlo + 5 >= 5 rows).  Stage 1 of the next row is
+// issued with stage 2 of the current one; the three-step loop body is entered at the slot that makes the last step end
+// a triple (the rolling state is symmetric under rotation of its slots).
+//   xb: shared address of this warp's two row buffers; yr / cr: keyframe row rlo-2 / table row rlo-2 (lane columns);
+//   out: single-frame volume at output row rlo - 4 (advanced every step, stored from the fifth step on); wstride = W
+template <int MODE>
+__device__ __forceinline__ void march_unit(const Stage1Ctx& c1, const Stage2Ctx& c2, const uint32_t xb, const int lane,
+                                           const float fv0, const int nsteps, uint32_t yr, uint32_t cr, float* out,
+                                           const int wstride) {
+    Stage2State st;
+    st.clear();
+    float fv = fv0;
+    uint32_t off = 0;                      // byte offset of the row buffer stage 2 reads next
+    const uint32_t xw = xb + 4 * (lane + 1), xr = xb + 8 * lane;
+    {
+        Taps t;
+        warp_row_issue<MODE>(c1, fv, t);
+        warp_row_finish(t, xw);
+    }
+    __syncwarp();
+    const int n = nsteps - 1;              // steps that also run stage 1 of the following row
+    int t = -((3 - n % 3) % 3);
+    int done = 0;                          // rows stage 2 has consumed
+    auto both = [&](auto tag) {
+        fv += 1.0f;
+        Taps tp;
+        if (MR_CV_SKIP != 4) warp_row_issue<MODE>(c1, fv, tp);
+        if (MR_CV_ORDER == 0 && MR_CV_SKIP != 4) warp_row_finish(tp, xw + (kXbBytes - off));
+        if (MR_CV_SKIP != 3) ssim_row<decltype(tag)::value>(st, c2, xr + off, yr, cr, out, done >= 4);
+        if (MR_CV_ORDER != 0 && MR_CV_SKIP != 4) warp_row_finish(tp, xw + (kXbBytes - off));
+        __syncwarp();
+        off = kXbBytes - off;
+        yr += kYRowBytes;
+        cr += kCRowBytes;
+        out += wstride;
+        ++done;
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    for (; t < n; t += 3) {
+        if (t >= 0) both(I0{});
+        if (t + 1 >= 0) both(I1{});
+        both(I2{});
+    }
+    if (MR_CV_SKIP != 3) ssim_row<0>(st, c2, xr + off, yr, cr, out, true);
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS)
+cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout L = make_layout(a.D, a.TH, a.F, a.use_tma);
+    float* win = reinterpret_cast<float*>(smem + L.win);
     float* ytile = reinterpret_cast<float*>(smem + L.ytile);
     float* cst = reinterpret_cast<float*>(smem + L.cst);
     float* pjs = reinterpret_cast<float*>(smem + L.pjs);
     float* zs = reinterpret_cast<float*>(smem + L.zs);
     unsigned char* vmask = smem + L.vmask;
     int* rowrng = reinterpret_cast<int*>(smem + L.rowrng);
+    short4* bbox = reinterpret_cast<short4*>(smem + L.bbox);
+    unsigned short* gid = reinterpret_cast<unsigned short*>(smem + L.gid);
+    unsigned char* uflag = smem + L.uflag;
+    GroupInfo* ginfo = reinterpret_cast<GroupInfo*>(smem + L.ginfo);
+    unsigned short* seq2g = reinterpret_cast<unsigned short*>(smem + L.seq2g);
+    int* nwin = reinterpret_cast<int*>(smem + L.nwin);
+    // [0] next unit, [1] number of windows, [2 + buf] finished units of the window in buffer buf, [2 + kBuf + buf] number of
+    // the last window whose TMA has been issued into buffer buf (-1: none)
+    int* ctr = reinterpret_cast<int*>(smem + L.ctr);
+    const uint32_t bars = smem_u32(smem + L.bars);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = a.H, W = a.W, D = a.D, TH = a.TH, F = a.F;
@@ -338,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
     const int v0 = blockIdx.y * TH;            // image row of tile row 0
     const size_t plane = (size_t)H * W;
     const int planei = H * W;
-    float* xbuf = reinterpret_cast<float*>(smem + L.xbuf) + warp * 3 * kRowStride;
+    float* xbuf = reinterpret_cast<float*>(smem + L.xbuf) + warp * 2 * 3 * kRowStride;
 
     // ---- keyframe tile (+0.5, monorec_model.py:232) and hoisted SSIM terms -------------------------------------
     const float* key = a.key + (size_t)b * 3 * plane;
@@ -347,53 +550,49 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
         int u = u0 + idx - 1, v = v0 - 2 + rr;
         float val = 0.f;
         if (u >= 0 && u < W && v >= 0 && v < H) val = __ldg(key + ch * plane + (size_t)v * W + u) + 0.5f;
-        ytile[(ch * (TH + 4) + rr) * kRowStride + idx] = val;
+        ytile[(rr * 3 + ch) * kRowStride + idx] = val;
     }
     for (int i = tid; i < D; i += kThreads) zs[i] = __ldg(a.depths + i);
-    if (lane < 3) { xbuf[lane * kRowStride] = 0.f; xbuf[lane * kRowStride + kTileCols + 1] = 0.f; }
+    if (lane < 6) {   // columns -1 and 64 of both row buffers stay zero
+        const int rb = lane / 3, ch = lane % 3;
+        xbuf[(rb * 3 + ch) * kRowStride] = 0.f;
+        xbuf[(rb * 3 + ch) * kRowStride + kTileCols + 1] = 0.f;
+    }
+    if (tid < 2 * F) rowrng[tid] = (tid & 1) ? -1 : TH;
+    if (tid < 12 * F) pjs[tid] = __ldg(a.proj + (size_t)b * F * 12 + tid);
+    if (tid < 2 + 2 * kBuf) ctr[tid] = (tid < 2 + kBuf) ? 0 : -1;
+    if (tid == 0 && a.use_tma) {
+        for (int i = 0; i < kBuf; ++i) mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    // table entry for the column pair (2j, 2j+1) of e-row er, channel ch: (mu_y[2j], mu_y[2j+1], sy2[2j], sy2[2j+1])
+    // table entry for the column pair (2j, 2j+1) of e-row er, channel ch: (Y[2j], Y[2j+1], Sg[2j], Sg[2j+1]) with
+    // Y = 9 mu_y = sum y, Sg = 81 (sigma_y + C2) = 9 sum y^2 - Y^2 + 81 C2
     for (int i = tid; i < 3 * (TH + 2) * kTileCols; i += kThreads) {
         int bc = i % kTileCols, t = i / kTileCols, er = t % (TH + 2), ch = t / (TH + 2);
-        const float* y = ytile + (ch * (TH + 4) + er) * kRowStride + bc;  // rows er..er+2, idx bc..bc+2
+        const float* y = ytile + (er * 3 + ch) * kRowStride + bc;  // rows er..er+2, idx bc..bc+2
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                float q = y[dy * kRowStride + dx];
+                float q = y[dy * 3 * kRowStride + dx];
                 s1 += q;
                 s2 = fmaf(q, q, s2);
             }
-        float mu = s1 * (1.0f / 9.0f);
-        float sy2 = fmaf(s2, 1.0f / 9.0f, -mu * mu) + kC2;
-        float* dst = cst + ((ch * (TH + 2) + er) * (kTileCols / 2) + (bc >> 1)) * 4 + (bc & 1);
-        dst[0] = mu;
-        dst[2] = sy2;
+        float* dst = cst + ((er * 3 + ch) * (kTileCols / 2) + (bc >> 1)) * 4 + (bc & 1);
+        dst[0] = s1;
+        dst[2] = fmaf(9.0f, s2, -s1 * s1) + 81.0f * kC2;
     }
 
     const float fW = (float)W, fH = (float)H;
-    const float sx_lo = -(fW + 1.f) * 0.5f, sx_hi = (3.f * fW - 1.f) * 0.5f;  // == grid clamp(-2, 2), monorec_model.py:208
-    const float sy_lo = -(fH + 1.f) * 0.5f, sy_hi = (3.f * fH - 1.f) * 0.5f;
-    const float2 fu2 = make_float2((float)(u0 + lane), (float)(u0 + lane + 32));
-    const float2 cw0 = bc2(a.cw0), cw1 = bc2(a.cw1), cw2 = bc2(a.cw2);
-    // per-lane smem bases for stage 2 (columns 2l-1 .. 2l+2 live at float index 2l .. 2l+3 of a row)
-    const float* ys_l = ytile + 2 * lane;
-    const float4* cs_l = reinterpret_cast<const float4*>(cst) + lane;
-    const int ych = (TH + 4) * kRowStride;        // ytile channel stride (floats)
-    const int cch = (TH + 2) * (kTileCols / 2);   // cst channel stride (float4)
-    // stage 2 writes the single-frame volume for output columns u0 + 2l, u0 + 2l + 1 (lanes 1..30)
-    const int ucol = u0 + 2 * lane;
-    const bool st0 = (lane >= 1) && (lane <= 30) && (ucol < W);
-    const bool st1 = (lane >= 1) && (lane <= 30) && (ucol + 1 < W);
-    const bool st_pair = st0 && st1 && ((W & 1) == 0);
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    const float sx_lo = -fW * 0.5f, sx_hi = 1.5f * fW;  // == grid clamp(-2, 2) in sample + 0.5 units, monorec_model.py:208
+    const float sy_lo = -fH * 0.5f, sy_hi = 1.5f * fH;
 
     // ---- validity pre-pass for every frame: valid_f(v,u) = interior(v,u) & all_d [ sample strictly inside
-    //      (1,W-2)x(1,H-2) ]  (monorec_model.py:212-219: bilinear sample of the interior mask != 0 for every plane) ----
-    if (tid < 2 * F) rowrng[tid] = (tid & 1) ? -1 : TH;
-    if (tid < 12 * F) pjs[tid] = __ldg(a.proj + (size_t)b * F * 12 + tid);
-    __syncthreads();
+    //      (1,W-2)x(1,H-2) ]  (monorec_model.py:212-219: bilinear sample of the interior mask != 0 for every plane).
+    //      The D samples of a pixel lie on one line and move monotonically with the depth while the denominator keeps
+    //      its sign, so the farthest and the nearest plane decide. -----------------------------------------------------
     for (int q = tid; q < F * TH * kTileCols; q += kThreads) {
         const int f = q / (TH * kTileCols), p = q - f * (TH * kTileCols);
         const int r = p >> 6, bc = p & 63;
@@ -406,12 +605,14 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
             const float ay = fmaf(m[4], fu, fmaf(m[5], fv, m[6]));
             const float az = fmaf(m[8], fu, fmaf(m[9], fv, m[10]));
             const float m03 = m[3], m13 = m[7], m23 = m[11];
-            for (int d = 0; d < D; ++d) {
-                const float z = zs[d];
-                const float inv = fast_rcp(fmaf(az, z, m23));
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float z = zs[k ? D - 1 : 0];
+                const float den = fmaf(az, z, m23);
+                const float inv = fast_rcp(den);
                 const float sx = fmaf(fmaf(ax, z, m03), inv, -0.5f);
                 const float sy = fmaf(fmaf(ay, z, m13), inv, -0.5f);
-                ok = ok && (sx > 1.0f) && (sx < fW - 2.0f) && (sy > 1.0f) && (sy < fH - 2.0f);
+                ok = ok && (den > 0.f) && (sx > 1.0f) && (sx < fW - 2.0f) && (sy > 1.0f) && (sy < fH - 2.0f);
             }
         }
         vmask[q] = ok ? 1 : 0;
@@ -419,49 +620,184 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
     }
     __syncthreads();
 
+    // ---- plan: source footprint of every unit (4 corners of the rows / columns its march touches), then windows ------
+    const int nunits = F * D;
+    for (int u = tid; u < nunits; u += kThreads) {
+        const int f = u / D, d = u - f * D;
+        const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
+        short4 bb = make_short4(0, 0, 0, 0);
+        unsigned char fl = 0;          // bit 0: footprint usable for a window, bit 1: strictly inside the image
+        if (rhi >= rlo && a.use_tma) {
+            const float* m = pjs + 12 * f;
+            const float z = zs[d];
+            float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+            bool good = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float fu = (float)(u0 + ((k & 1) ? kTileCols - 1 : 0));
+                const float fv = (float)(v0 + ((k & 2) ? rhi + 2 : rlo - 2));
+                const float cx = fmaf(fmaf(m[0], fu, fmaf(m[1], fv, m[2])), z, m[3]);
+                const float cy = fmaf(fmaf(m[4], fu, fmaf(m[5], fv, m[6])), z, m[7]);
+                const float cz = fmaf(fmaf(m[8], fu, fmaf(m[9], fv, m[10])), z, m[11]);
+                good = good && (cz > 1e-6f);
+                const float inv = 1.0f / cz;
+                const float sx = fminf(fmaxf(cx * inv, sx_lo), sx_hi) - 0.5f, sy = fminf(fmaxf(cy * inv, sy_lo), sy_hi) - 0.5f;
+                xmin = fminf(xmin, sx); xmax = fmaxf(xmax, sx);
+                ymin = fminf(ymin, sy); ymax = fmaxf(ymax, sy);
+            }
+            if (good) {
+                // one pixel of slack on every side for the rounding differences between this estimate and stage 1
+                // (the window origin is rounded down to a multiple of 4 pixels: TMA wants the innermost box coordinate
+                // 16-byte aligned -- measured: tools/experiments_r02/tma_probe.cu -- negative coordinates are fine)
+                const int xl = (max((int)floorf(xmin) - 1, -2) >> 2) << 2, xh = min((int)floorf(xmax) + 2, W + 1);
+                const int yl = max((int)floorf(ymin) - 1, -2), yh = min((int)floorf(ymax) + 2, H + 1);
+                if (xh >= xl && yh >= yl && xh - xl < kPitch && yh - yl < kWinRows) {
+                    fl = 1;
+                    if (xmin >= 0.05f && xmax <= fW - 1.05f && ymin >= 0.05f && ymax <= fH - 1.05f) fl = 3;
+                    bb = make_short4((short)xl, (short)xh, (short)yl, (short)yh);
+                }
+            }
+        }
+        bbox[u] = bb;
+        uflag[u] = fl;
+        gid[u] = 0xFFFF;
+    }
+    __syncthreads();
+    if (tid < F) {
+        // greedy runs of consecutive planes whose union still fits one window
+        const int f = tid;
+        int ng = 0;
+        const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
+        if (rhi >= rlo && a.use_tma) {
+            int d = 0;
+            while (d < D) {
+                if (!(uflag[f * D + d] & 1)) { ++d; continue; }
+                short4 g = bbox[f * D + d];
+                int e = d + 1;
+                while (e < D && (uflag[f * D + e] & 1)) {
+                    const short4 o = bbox[f * D + e];
+                    const int xl = min(g.x, o.x), xh = max(g.y, o.y), yl = min(g.z, o.z), yh = max(g.w, o.w);
+                    if (xh - xl >= kPitch || yh - yl >= kWinRows) break;
+                    g = make_short4((short)xl, (short)xh, (short)yl, (short)yh);
+                    ++e;
+                }
+                if (e - d >= kMinGroup) {
+                    GroupInfo gi;
+                    gi.wx0 = g.x; gi.wy0 = g.z;
+                    gi.nrows = (short)(((g.w - g.z + 1) + kBoxRows - 1) / kBoxRows * kBoxRows);
+                    gi.f = (short)f; gi.count = (short)(e - d); gi.seq = (short)ng; gi.pad0 = gi.pad1 = 0;
+                    ginfo[f * D + ng] = gi;
+                    for (int k = d; k < e; ++k) gid[f * D + k] = (unsigned short)(f * D + ng);
+                    ++ng;
+                }
+                d = e;
+            }
+        }
+        nwin[f] = ng;
+    }
+    __syncthreads();
+    if (tid < F) {
+        int base = 0;
+        for (int k = 0; k < tid; ++k) base += nwin[k];
+        for (int g = 0; g < nwin[tid]; ++g) {
+            ginfo[tid * D + g].seq = (short)(base + g);
+            seq2g[base + g] = (unsigned short)(tid * D + g);
+        }
+        if (tid == F - 1) ctr[1] = base + nwin[tid];
+    }
+    __syncthreads();
+
+    // window `seq` -> buffer seq % kBuf: 3 channel planes of nrows rows, TMA boxes of kBoxRows rows
+    auto issue_window = [&](int seq) {
+        const GroupInfo gi = ginfo[seq2g[seq]];
+        const int buf = seq % kBuf;
+        const uint32_t bar = bars + 8 * buf;
+        const uint32_t dst = smem_u32(win + (size_t)buf * kWinFloats);
+        *reinterpret_cast<volatile int*>(&ctr[2 + kBuf + buf]) = seq;
+        mbar_expect_tx(bar, (uint32_t)(3 * gi.nrows * kPitch * 4));
+        for (int ch = 0; ch < 3; ++ch)
+            for (int r8 = 0; r8 < gi.nrows; r8 += kBoxRows)
+                tma_load_3d(dst + (uint32_t)((ch * kWinRows + r8) * kPitch * 4), &maps.m[gi.f], bar, gi.wx0, gi.wy0 + r8, b * 3 + ch);
+    };
+    if (tid == 0 && a.use_tma) {
+        const int nw = ctr[1];
+        for (int s = 0; s < kBuf && s < nw; ++s) issue_window(s);
+    }
+
+    const float2 fu2 = make_float2((float)(u0 + lane), (float)(u0 + lane + 32));
+    // stage 2 writes the single-frame volume for output columns u0 + 2l, u0 + 2l + 1 (lanes 1..30)
+    const int ucol = u0 + 2 * lane;
+    const bool st0 = (lane >= 1) && (lane <= 30) && (ucol < W);
+    const bool st1 = (lane >= 1) && (lane <= 30) && (ucol + 1 < W);
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+
     // ---- march over the F*D (frame, plane) units; no CTA-wide barrier in here ------------------------------------
     Stage2Ctx c2;
-    c2.ys_l = ys_l; c2.cs_l = cs_l; c2.ych = ych; c2.cch = cch;
-    c2.cw0 = cw0; c2.cw1 = cw1; c2.cw2 = cw2;
-    c2.W = W; c2.rows_left = H - v0; c2.st_pair = st_pair; c2.st0 = st0; c2.st1 = st1; c2.pol_keep = pol_keep;
+    c2.cw0 = bc2(a.cw0); c2.cw1 = bc2(a.cw1); c2.cw2 = bc2(a.cw2);
+    c2.st0 = st0; c2.st1 = st1; c2.pairflag = (st0 && st1 && ((W & 1) == 0)) ? 1 : 0; c2.pol_keep = pol_keep;
     Stage1Ctx c1;
-    c1.W = W; c1.H = H; c1.planei = planei; c1.v0 = v0; c1.lane = lane;
+    c1.W = W; c1.H = H; c1.planei = planei;
     c1.sx_lo = sx_lo; c1.sx_hi = sx_hi; c1.sy_lo = sy_lo; c1.sy_hi = sy_hi;
-#ifndef MR_CV_SKIP
-#define MR_CV_SKIP 0     // timing experiments only: 1 = no march, 2 = no per-pixel phase, 3 = march without stage 2, 4 = march without stage 1
-#endif
-    for (int unit = warp; unit < F * D && MR_CV_SKIP != 1; unit += kWarps) {
+    // per-lane shared addresses for stage 2 (columns 2l-1 .. 2l+2 live at float index 2l .. 2l+3 of a row)
+    const uint32_t xb_s = smem_u32(xbuf);
+    const uint32_t ys_s = smem_u32(ytile) + 8 * lane;
+    const uint32_t cs_s = smem_u32(cst) + 16 * lane;
+    const uint32_t win_s = smem_u32(win);
+    for (; MR_CV_SKIP != 1;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(&ctr[0], 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= nunits) break;
         const int f = unit / D, d = unit - f * D;
         const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
         if (rhi < rlo) continue;  // no valid pixel of this tile for frame f: the per-pixel phase zero-fills
-        setup_stage1(c1, pjs + 12 * f, a.frames[f] + (size_t)b * 3 * plane, zs[d], fu2);
-        c1.img4 = PACKED ? a.packed + ((size_t)f * a.B + b) * plane : nullptr;
-        Stage2State st;
-        st.clear();
-        c2.out_d = a.sfcv + (((size_t)f * a.B + b) * D + d) * plane + (size_t)v0 * W + ucol;
+        setup_stage1(c1, pjs + 12 * f, zs[d], fu2);
         const int nsteps = rhi - rlo + 5;
-        auto step = [&](auto tag, auto stage, const int t) {
-            if (MR_CV_SKIP != 4) warp_row<PACKED>(c1, rlo - 2 + t, xbuf);
+        const float fv0 = (float)(v0 + rlo - 2);
+        const uint32_t yr = ys_s + rlo * kYRowBytes;          // tile row rlo-2 is keyframe-tile row rlo
+        // the SSIM row of step t is tile row rlo-3+t, whose table row is rlo-2+t (t = 0, 1 read throw-away rows, possibly
+        // in front of the table: still inside this CTA's shared memory, see make_layout)
+        const uint32_t cr = cs_s + (rlo - 2) * kCRowBytes;
+        float* out = a.sfcv + (((size_t)f * a.B + b) * D + d) * plane + ((ptrdiff_t)(v0 + rlo - 4) * W + ucol);
+        const unsigned g = gid[unit];
+        if (g != 0xFFFFu) {
+            const GroupInfo gi = ginfo[g];
+            const int buf = gi.seq % kBuf;
+            // A parity wait is only meaningful on the phase in progress or the one before: first make sure this window's
+            // load has been issued (the buffer's previous window is then complete and consumed), then wait for its bytes.
+            {
+                const volatile int* armed = &ctr[2 + kBuf + buf];
+                for (uint32_t spin = 0; *armed < gi.seq; ++spin)
+                    if (spin > (1u << 24)) __trap();
+            }
+            mbar_wait(bars + 8 * buf, (uint32_t)((gi.seq / kBuf) & 1));
+            const uint32_t wb = win_s + (uint32_t)buf * (kWinFloats * 4);
+            if (uflag[unit] & 2) {
+                // tap address = wb + 4 ((bits(ty) - kMagicBits - wy0) kPitch + bits(tx) - kMagicBits - wx0), mod 2^32
+                c1.kaddr = wb - 4u * ((uint32_t)(kMagicBits + gi.wy0) * kPitch + (uint32_t)(kMagicBits + gi.wx0));
+                march_unit<0>(c1, c2, xb_s, lane, fv0, nsteps, yr, cr, out, W);
+            } else {
+                c1.kaddr = wb - 4u * ((uint32_t)(int)gi.wy0 * kPitch + (uint32_t)(int)gi.wx0);
+                march_unit<1>(c1, c2, xb_s, lane, fv0, nsteps, yr, cr, out, W);
+            }
+            // hand the buffer on: the last unit of the window re-arms it with the window after next
+            if (lane == 0) {
+                __threadfence_block();
+                const int fin = atomicAdd(&ctr[2 + buf], 1) + 1;
+                if (fin == gi.count) {
+                    ctr[2 + buf] = 0;
+                    __threadfence_block();
+                    if (gi.seq + kBuf < ctr[1]) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue_window(gi.seq + kBuf);
+                    }
+                }
+            }
             __syncwarp();
-            if (MR_CV_SKIP != 3) ssim_row<decltype(tag)::value, decltype(stage)::value>(st, c2, rlo - 2 + t, xbuf + 2 * lane);
-            __syncwarp();
-        };
-        using I0 = std::integral_constant<int, 0>;
-        using I1 = std::integral_constant<int, 1>;
-        using I2 = std::integral_constant<int, 2>;
-        // window fill (nsteps >= 5 always), then the branch-free steady state
-        step(I0{}, I0{}, 0);
-        step(I1{}, I0{}, 1);
-        step(I2{}, I1{}, 2);
-        step(I0{}, I1{}, 3);
-        int t = 4;
-        for (; t + 2 < nsteps; t += 3) {
-            step(I1{}, I2{}, t);
-            step(I2{}, I2{}, t + 1);
-            step(I0{}, I2{}, t + 2);
+        } else {
+            c1.img = a.frames[f] + (size_t)b * 3 * plane;
+            march_unit<2>(c1, c2, xb_s, lane, fv0, nsteps, yr, cr, out, W);
         }
-        if (t < nsteps) step(I1{}, I2{}, t);
-        if (t + 1 < nsteps) step(I2{}, I2{}, t + 1);
     }
     __syncthreads();  // the marching warps' global stores are visible to the whole CTA from here on
 
@@ -476,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS) cost_volume_kernel(
         if (!own) continue;
         const size_t pix = (size_t)v * W + u;
         float* cv_out = a.cv + (size_t)b * D * plane + pix;
-        for (int d0 = 0; d0 < D; d0 += kChunk) {   // one pass when D <= kChunk (every shipped config)
+        for (int d0 = 0; d0 < D; d0 += kChunk) {   // one pass when D <= kChunk
             float acc[kChunk];
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
@@ -602,23 +938,27 @@ __global__ void projection_tables_kernel(const float* kf_pose, const float* kf_K
     }
 }
 
-// Source frames re-laid as (r,g,b,0) pixels so that a bilinear tap is one 16-byte load (see warp_row<true>).
-__global__ void repack_frames_kernel(PtrPack frames, float4* __restrict__ packed, int B, int HW, int b0) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= HW) return;
-    const int b = b0 + blockIdx.y, f = blockIdx.z;
-    const float* src = frames.p[f] + (size_t)b * 3 * HW + p;
-    packed[((size_t)f * B + b) * HW + p] = make_float4(__ldg(src), __ldg(src + HW), __ldg(src + 2 * (size_t)HW), 0.f);
-}
-
-#ifndef MR_CV_TILE_ROWS
-#define MR_CV_TILE_ROWS 16
-#endif
-int pick_tile_rows(int D, int F) {
+int pick_tile_rows(int D, int F, int use_tma) {
     const int limit = 227 * 1024;
     for (int th = MR_CV_TILE_ROWS; th >= 2; th >>= 1)
-        if (make_layout(D, th, F).total <= limit) return th;
+        if (make_layout(D, th, F, use_tma).total <= limit) return th;
     return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;   // benign race: every thread resolves the same pointer
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
 }
 
 }  // namespace
@@ -646,14 +986,14 @@ extern "C" int mr_projection_tables(const float* keyframe_pose, const float* key
 
 int mr::launch_cost_volume(const float* keyframe, const float* const* frames, const float* proj,
                            const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H, int W,
-                           float alpha, const float* chan_w, int b_begin, int b_count, void* workspace,
-                           long long workspace_bytes, cudaStream_t stream) {
+                           float alpha, const float* chan_w, int b_begin, int b_count, int gather_only,
+                           cudaStream_t stream) {
     MR_REQUIRE(keyframe && frames && proj && depths && out_cv && out_sfcv, "mr_cost_volume_fwd: null pointer");
     MR_REQUIRE(b_begin >= 0 && b_count >= 1 && b_begin + b_count <= B, "mr_cost_volume_fwd: bad batch range");
-    MR_REQUIRE(B >= 1 && B <= 65535, "mr_cost_volume_fwd: batch %d out of range", B);
+    MR_REQUIRE(B >= 1 && B <= 21845, "mr_cost_volume_fwd: batch %d out of range", B);
     MR_REQUIRE(F >= 1 && F <= MR_MAX_FRAMES, "mr_cost_volume_fwd: 1 <= F <= %d required (got %d)", MR_MAX_FRAMES, F);
     MR_REQUIRE(D >= 2 && D <= 128, "mr_cost_volume_fwd: 2 <= D <= 128 required (got %d)", D);
-    MR_REQUIRE(H >= 5 && W >= 5, "mr_cost_volume_fwd: image too small (%dx%d)", H, W);
+    MR_REQUIRE(H >= 5 && W >= 5 && H <= 16384 && W <= 16384, "mr_cost_volume_fwd: image size %dx%d out of range", H, W);
     CvArgs a{};
     a.key = keyframe;
     for (int f = 0; f < F; ++f) {
@@ -662,53 +1002,74 @@ int mr::launch_cost_volume(const float* keyframe, const float* const* frames, co
     }
     a.proj = proj; a.depths = depths; a.cv = out_cv; a.sfcv = out_sfcv;
     a.B = B; a.F = F; a.D = D; a.H = H; a.W = W; a.b0 = b_begin;
-    a.TH = pick_tile_rows(D, F);
+    // TMA addresses the frames as (W, H, 3B) tensors: the row pitch must be a multiple of 16 bytes and the base 16-byte
+    // aligned; otherwise (ragged widths) every unit takes the global gather of the same kernel.
+    static CvMaps maps;   // storage for the by-value kernel parameter; rebuilt on every call before the launch reads it
+    CvMaps local{};
+    a.use_tma = 0;
+    EncodeTiledFn encode = gather_only ? nullptr : get_encode_fn();
+    if (encode != nullptr && (W % 4) == 0) {
+        bool ok = true;
+        for (int f = 0; f < F && ok; ++f) {
+            if (reinterpret_cast<uintptr_t>(frames[f]) & 15) { ok = false; break; }
+            const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)3 * B};
+            const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+            const cuuint32_t box[3] = {(cuuint32_t)kPitch, (cuuint32_t)kBoxRows, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = encode(&local.m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(frames[f]), gdim, gstr,
+                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            ok = (r == CUDA_SUCCESS);
+        }
+        if (ok) {
+            for (int f = F; f < MR_MAX_FRAMES; ++f) local.m[f] = local.m[0];
+            a.use_tma = 1;
+        }
+    }
+    (void)maps;
+    a.TH = pick_tile_rows(D, F, a.use_tma);
     MR_REQUIRE(a.TH > 0, "mr_cost_volume_fwd: no tile height fits shared memory for D=%d F=%d", D, F);
     a.alpha = alpha;
     a.inv_dm1 = (float)(1.0 / (double)(D - 1));
     const float def_w[3] = {5.f / 32.f, 16.f / 32.f, 11.f / 32.f};  // monorec_model.py:133
     const float* cw = chan_w ? chan_w : def_w;
     a.cw0 = cw[0] / 9.f; a.cw1 = cw[1] / 9.f; a.cw2 = cw[2] / 9.f;  // monorec_model.py:141 (weights / patch_size^2)
-    const SmemLayout L = make_layout(D, a.TH, F);
+    const SmemLayout L = make_layout(D, a.TH, F, a.use_tma);
     dim3 grid((W + kOutCols - 1) / kOutCols, (H + a.TH - 1) / a.TH, b_count);
-    if (workspace != nullptr) {
-        MR_REQUIRE(workspace_bytes >= mr_cost_volume_workspace_bytes(B, F, H, W),
-                   "mr_cost_volume_fwd_ws: workspace too small (%lld < %lld bytes)", workspace_bytes,
-                   mr_cost_volume_workspace_bytes(B, F, H, W));
-        MR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "mr_cost_volume_fwd_ws: workspace must be 16-byte aligned");
-        a.packed = static_cast<const float4*>(workspace);
-        PtrPack fp{};
-        for (int f = 0; f < F; ++f) fp.p[f] = frames[f];
-        dim3 rgrid((H * W + 255) / 256, b_count, F);
-        repack_frames_kernel<<<rgrid, 256, 0, stream>>>(fp, static_cast<float4*>(workspace), B, H * W, b_begin);
-        MR_LAUNCH_CHECK("repack_frames_kernel");
-        MR_CUDA(cudaFuncSetAttribute(cost_volume_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        cost_volume_kernel<true><<<grid, kThreads, L.total, stream>>>(a);
-    } else {
-        MR_CUDA(cudaFuncSetAttribute(cost_volume_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        cost_volume_kernel<false><<<grid, kThreads, L.total, stream>>>(a);
+    static int smem_set = 0;   // the attribute is per function and per device context; setting it again is harmless
+    if (smem_set < L.total) {
+        MR_CUDA(cudaFuncSetAttribute(cost_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        smem_set = 227 * 1024;
     }
+    cost_volume_kernel<<<grid, kThreads, L.total, stream>>>(a, local);
     MR_LAUNCH_CHECK("cost_volume_kernel");
     return MR_OK;
 }
 
 extern "C" long long mr_cost_volume_workspace_bytes(int B, int F, int H, int W) {
-    if (B < 1 || F < 1 || H < 1 || W < 1) return 0;
-    return (long long)F * B * H * W * 16;
+    (void)B; (void)F; (void)H; (void)W;
+    return 0;   // since 0.2 the kernel stages source windows by TMA from the frames themselves: no re-laid copy is needed
 }
 
 extern "C" int mr_cost_volume_fwd_ws(const float* keyframe, const float* const* frames, const float* proj,
                                      const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H, int W,
                                      float alpha, const float* chan_w, void* workspace, long long workspace_bytes,
                                      void* stream) {
-    MR_REQUIRE(workspace != nullptr, "mr_cost_volume_fwd_ws: null workspace");
-    return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0, B,
-                                  workspace, workspace_bytes, (cudaStream_t)stream);
+    (void)workspace; (void)workspace_bytes;
+    return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0, B, 0,
+                                  (cudaStream_t)stream);
 }
 
 extern "C" int mr_cost_volume_fwd(const float* keyframe, const float* const* frames, const float* proj,
                                   const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H,
                                   int W, float alpha, const float* chan_w, void* stream) {
     return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0,
-                                  B, nullptr, 0, (cudaStream_t)stream);
+                                  B, 0, (cudaStream_t)stream);
+}
+
+extern "C" int mr_cost_volume_fwd_gather(const float* keyframe, const float* const* frames, const float* proj,
+                                         const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H,
+                                         int W, float alpha, const float* chan_w, void* stream) {
+    return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0,
+                                  B, 1, (cudaStream_t)stream);
 }

@@ -8,7 +8,7 @@
 namespace {
 
 struct HostPlan {
-    size_t img, mats, proj, depths, cv, sfcv, packed, total;  // byte offsets into the workspace
+    size_t img, mats, proj, depths, cv, sfcv, total;  // byte offsets into the workspace
 };
 
 HostPlan plan(int B, int F, int D, int H, int W) {
@@ -21,7 +21,6 @@ HostPlan plan(int B, int F, int D, int H, int W) {
     p.depths = off; off = al(off + (size_t)D * 4);
     p.cv = off;     off = al(off + (size_t)B * D * H * W * 4);
     p.sfcv = off;   off = al(off + (size_t)F * B * D * H * W * 4);
-    p.packed = off; off = al(off + (size_t)F * B * H * W * 16);
     p.total = off;
     return p;
 }
@@ -109,8 +108,7 @@ extern "C" int mr_cost_volume_host(const float* h_keyframe, const float* h_frame
                 MR_CUDA(cudaMemcpyAsync(d_frames + o, h_frames + o, img1 * 4, cudaMemcpyHostToDevice, s));
             }
             MR_CUDA(cudaStreamWaitEvent(s, ring.ready, 0));
-            rc = mr::launch_cost_volume(d_key, fp, d_proj, d_depths, d_cv, d_sfcv, B, F, D, H, W, alpha, nullptr, b, 1, ws + p.packed,
-                                        (long long)F * B * H * W * 16, s);
+            rc = mr::launch_cost_volume(d_key, fp, d_proj, d_depths, d_cv, d_sfcv, B, F, D, H, W, alpha, nullptr, b, 1, 0, s);
             if (rc != MR_OK) return rc;
             MR_CUDA(cudaMemcpyAsync(h_out_cv + b * vol1, d_cv + b * vol1, vol1 * 4, cudaMemcpyDeviceToHost, s));
             for (int f = 0; f < F; ++f) {

@@ -60,7 +60,7 @@ def test_header_is_plain_c_and_a_c_consumer_links(tmp_path):
                    '    if (mr_sizeof_conv_desc() != (int)sizeof d) return 2;\n'
                    '    if (mr_conv2d_nhwc_tc(0, 16, 32, 0, 0) == MR_OK) return 3;\n'
                    '    if (strstr(mr_last_error(), "null descriptor") == 0) return 4;\n'
-                   '    if (mr_cost_volume_workspace_bytes(8, 4, 256, 512) <= 0) return 5;\n'
+                   '    if (mr_cost_volume_host_workspace(8, 4, 32, 256, 512) <= 0) return 5;\n'
                    '    printf("%d\\n", mr_version());\n    return 0;\n}\n')
     exe = tmp_path / "consumer"
     libdir = _lib.LIB_PATH.parent

@@ -191,19 +191,25 @@ def test_hires_config_small_batch():
     assert (cvp - cv).abs().max() <= 1e-5
 
 
-def test_packed_and_planar_gather_are_bit_identical():
-    """mr_cost_volume_fwd_ws ((r,g,b,0)-packed source copies, one 16-byte load per tap) == mr_cost_volume_fwd (planar)."""
+@pytest.mark.parametrize("B,F,H,W", [(2, 3, 96, 200), (1, 4, 256, 512)])
+def test_tma_windows_and_global_gather_agree(B, F, H, W):
+    """mr_cost_volume_fwd (TMA-staged windows) == mr_cost_volume_fwd_gather (taps from global memory): same formula, same
+    validity; the two interpolation code paths may differ in the last bits only."""
     from monorec_b200.cost_volume import CostVolumeModule
     from monorec_b200.synthetic import make_inputs, to_device
-    data = make_inputs(2, 3, 96, 200, seed=55)
+    data = make_inputs(B, F, H, W, seed=55)
     outs = []
-    for packed in (True, False):
+    for tma in (True, False):
         d = to_device(data, "cuda:0")
         d["_cv_range"] = (0.0025, 0.33, 32)
         m = CostVolumeModule()
-        m.packed_gather = packed
+        m.tma_windows = tma
         o = m(d)
         torch.cuda.synchronize()
         outs.append((o["cost_volume"].cpu(), [s.cpu() for s in o["single_frame_cvs"]]))
-    assert torch.equal(outs[0][0], outs[1][0])
-    assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal((a == 0).all(1), (b == 0).all(1))   # same validity (a plane stack that is exactly 0)
+        d = (a - b).abs()
+        assert d.max() <= 5e-5, f"single-frame volumes differ by {d.max().item():.3e} ({int((d > 2e-6).sum())} values > 2e-6)"
+    d = (outs[0][0] - outs[1][0]).abs()
+    assert d.max() <= 1e-4, f"fused volumes differ by {d.max().item():.3e}"

@@ -1,0 +1,11 @@
+#!/bin/bash
+# K1: parity of the default build, then CUDA-event timings of every variant library under monorec_b200/variants/
+mkdir -p gpurun_out
+exec > >(tee gpurun_out/k1_variants.log) 2>&1
+timeout 600 python -m pytest tests/test_cost_volume_gpu.py -q -m gpu 2>&1 | tail -6
+echo "== default"; timeout 300 python tools/time_cv.py 2>&1 | tail -2
+timeout 300 python tools/time_cv.py 4 6 64 512 1024 5 2>&1 | tail -2
+for lib in monorec_b200/variants/*.so; do
+  echo "== $(basename $lib)"
+  MONOREC_B200_LIB=$PWD/$lib timeout 300 python tools/time_cv.py 2>&1 | tail -2 | head -1
+done

@@ -6,10 +6,10 @@ import sys; sys.path.insert(0, '.')
 import torch
 from monorec_b200.cost_volume import CostVolumeModule
 from monorec_b200.synthetic import make_inputs, to_device
-for (B, F, D, H, W) in [(1, 2, 8, 37, 61), (1, 3, 32, 48, 333), (2, 2, 16, 40, 130)]:
+for (B, F, D, H, W) in [(1, 2, 8, 37, 61), (1, 3, 32, 48, 332), (2, 2, 16, 40, 132), (1, 2, 32, 64, 128)]:
     d = to_device(make_inputs(B, F, H, W, seed=3), "cuda:0"); d["_cv_range"] = (0.0025, 0.33, D)
-    for packed in (True, False):
-        m = CostVolumeModule(); m.packed_gather = packed
+    for tma in (True, False):
+        m = CostVolumeModule(); m.tma_windows = tma
         o = m(d); torch.cuda.synchronize()
 print("k1 done")
 PY
