@@ -9,3 +9,4 @@ for lib in monorec_b200/variants/*.so; do
   echo "== $(basename $lib)"
   MONOREC_B200_LIB=$PWD/$lib timeout 300 python tools/time_cv.py 2>&1 | tail -2 | head -1
 done
+bash tools/gpu_sanitize.sh 2>&1 | grep -v "^$" | grep "k1" | tail -4
