@@ -148,14 +148,8 @@ int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
  * 32 channels (64-byte swizzle rows); the MMA is kind::f16; dst_dtype selects half or float output.
  * Stride-1 layers whose packed weights fit in shared memory twice per SM run on the "halo" variant of the kernel (same
  * results).  Tuning switches (environment, read once): MONOREC_B200_TC_HALO=0|1|2, MONOREC_B200_TC_HALO_F16=0|1,
- * MONOREC_B200_TC_QUAD=0|1, MONOREC_B200_TC_CTAS=n; experimental, off by default: MONOREC_B200_TC_EPI=1 (staged epilogue),
- * MONOREC_B200_TC_HALO_K32=1 (64-byte rows in the halo kernel), MONOREC_B200_TC_HALO_EPI8=1 (8 epilogue warps). */
+ * MONOREC_B200_TC_CTAS=n. */
 int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream);
-/* The same with a residual input: out = act(conv + bias + residual), `residual` laid out and typed exactly like the
- * destination slice (same dst_H / dst_W / dst_c / dst_coff and steps) -- the second convolution of a ResNet basic block
- * (torchvision resnet.py BasicBlock.forward; reference use: model/monorec/monorec_model.py:95-129).  Implemented by the staged
- * epilogue only (MONOREC_B200_TC_EPI=1, experimental): needs 16-byte aligned channel slices and a none / leaky activation. */
-int mr_conv2d_nhwc_tc_res(const mr_conv_desc* desc, const void* residual, int n_pad, int k_pad, int round_out, void* stream);
 /* sizeof(mr_conv_desc) as compiled into the library (bindings check their mirror of the struct against it). */
 int mr_sizeof_conv_desc(void);
 
@@ -172,10 +166,6 @@ int mr_max_over_frames_f16(const void* src, void* dst, int F, long long n_per_fr
 int mr_cast_f32_to_f16(const float* src, void* dst, long long n, void* stream);
 /* nn.MaxPool2d(2) on NHWC (monorec_model.py:304-316). H and W must be even. */
 int mr_maxpool2_nhwc(const float* src, float* dst, int B, int H, int W, int C, void* stream);
-/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC (torchvision resnet.py: the stem's pooling): output
- * ceil(H/2) x ceil(W/2) for even sizes; taps outside the image are ignored.  C % 4 == 0 (float) / C % 8 == 0 (half). */
-int mr_maxpool3s2_nhwc(const float* src, float* dst, int B, int H, int W, int C, void* stream);
-int mr_maxpool3s2_nhwc_f16(const void* src, void* dst, int B, int H, int W, int C, void* stream);
 /* Element-wise max over the leading axis: dst[n] = max_f src[f*n_per_frame + n]  (monorec_model.py:362-365). */
 int mr_max_over_frames(const float* src, float* dst, int F, long long n_per_frame, void* stream);
 /* out[b,d,p] = volume[b,d,p] * (1 - mask[b,p])   (monorec_model.py:713, NCHW volume [B,D,HW], mask [B,HW]). */

@@ -23,14 +23,13 @@ KC = 32            # channels per K chunk of the tensor-core kernel (csrc/conv_t
 # "f16" = tcgen05 kind::f16 with half NHWC activations and weights (fp32 accumulate; BASELINE config 3),
 # "fp32" = CUDA-core FMA kernel (bit-level parity path).  1-channel heads always use the CUDA-core dot-product kernel.
 MODE = os.environ.get("MONOREC_B200_CONV", "tf32").lower()
-# half sources of <= 32 channels: 32-channel K chunks (SWIZZLE_64B rows).  Stride-1 layers of that kind go to the halo kernel
-# instead (csrc/conv_tc.cu, faster still), which needs 128-byte rows, unless MONOREC_B200_TC_HALO_F16=0 / MONOREC_B200_TC_HALO=0.
+# half sources of <= 32 channels: 32-channel K chunks (SWIZZLE_64B rows), in the tap-refetch kernel and inside the halo box alike
+# (round 2: 429 -> 203 us on the 32->32 3x3 layer over the single-frame volumes).
 K32 = os.environ.get("MONOREC_B200_TC_K32", "1") != "0"
 HALO_F16 = os.environ.get("MONOREC_B200_TC_HALO_F16", "1") != "0" and os.environ.get("MONOREC_B200_TC_HALO", "") != "0"
-HALO_K32 = os.environ.get("MONOREC_B200_TC_HALO_K32", "0") != "0"   # experimental: 64-byte rows inside the halo box as well
-# experimental: the single-channel layers (1x1 mask classifier, the four 3x3 depth heads) on the tensor cores too (Cout padded
-# to 16) instead of the CUDA-core per-pixel kernel, which takes 0.45 ms of a half-mode forward
-TC_HEADS = os.environ.get("MONOREC_B200_TC_HEADS", "0") != "0"
+# the single-channel layers (1x1 mask classifier, the four 3x3 depth heads) run on the tensor cores too in the tf32 / f16
+# modes (Cout padded to 16): 5.93 -> 5.83 ms per half-mode forward at B=8 against the CUDA-core per-pixel kernel (round 2)
+TC_HEADS = True
 DT_F32, DT_F16 = 0, 1
 
 
@@ -194,17 +193,6 @@ def maxpool2(x):
     return out
 
 
-def maxpool3s2(x):
-    """nn.MaxPool2d(3, stride=2, padding=1) on NHWC (the ResNet stem's pooling)."""
-    lib = _lib.load()
-    B, H, W, C = x.shape
-    out = torch.empty(B, (H + 1) // 2, (W + 1) // 2, C, device=x.device, dtype=x.dtype)
-    fn, name = (lib.mr_maxpool3s2_nhwc_f16, "mr_maxpool3s2_nhwc_f16") if x.dtype == torch.float16 else (lib.mr_maxpool3s2_nhwc, "mr_maxpool3s2_nhwc")
-    with torch.cuda.device(x.device):
-        _lib.check(fn(x.data_ptr(), out.data_ptr(), B, H, W, C, _stream(x)), name)
-    return out
-
-
 def max_over_frames(x, frames):
     """x: [frames*B, ...] -> [B, ...] element-wise max over the leading frame axis."""
     if frames == 1:
@@ -282,28 +270,25 @@ class PackedConv:
 
     def wtc(self, half=False):
         if half not in self._wtc:
-            self._wtc[half] = pack_tc_weight(self._w_src, self.src_c, half=half,
-                                             allow_k32=HALO_K32 or not (HALO_F16 and tuple(self.stride) == (1, 1)))
+            self._wtc[half] = pack_tc_weight(self._w_src, self.src_c, half=half, allow_k32=True)
         return self._wtc[half]
 
-    def __call__(self, srcs, out=None, out_hw=None, final=False, residual=None, out_coff=0):
-        """residual: tensor shaped like the output, added before the activation (tensor-core path, staged epilogue only);
-        out_coff: first channel of the slice of `out` this layer writes."""
+    def __call__(self, srcs, out=None, out_hw=None, final=False, out_coff=0):
+        """out_coff: first channel of the slice of `out` this layer writes (tensor-core path)."""
         assert tuple(s.shape[3] for s in srcs) == self.src_c, (tuple(s.shape[3] for s in srcs), self.src_c)
         if MODE == "f16" and srcs[0].dtype == torch.float16:
             if self.tc_ok_f16:
-                return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=False, half=True, out_f32=final,
-                                 residual=residual, out_coff=out_coff)
+                return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=False, half=True, out_f32=final, out_coff=out_coff)
             assert self.cout == 1, "f16 mode: only the single-channel heads run on the CUDA-core kernel"
         if MODE == "tf32" and self.tc_ok:
-            return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=not final, residual=residual, out_coff=out_coff)
-        if residual is not None or out_coff:
-            raise NotImplementedError("monorec_b200.conv: residual inputs / channel-slice outputs need the tensor-core path")
+            return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=not final, out_coff=out_coff)
+        if out_coff:
+            raise NotImplementedError("monorec_b200.conv: channel-slice outputs need the tensor-core path")
         return conv2d(srcs, self.w32, self.bias, self.kh, self.kw, stride=self.stride, act=self.act, act_a=self.act_a,
                       act_b=self.act_b, out=out, pad=self.pad, out_hw=out_hw, out_step=self.out_step, out_off=self.out_off)
 
 
-def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f32=False, residual=None, out_coff=0):
+def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f32=False, out_coff=0):
     """Tensor-core launch (csrc/conv_tc.cu) of a PackedConv."""
     lib = _lib.load()
     x0 = srcs[0]
@@ -335,12 +320,7 @@ def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f3
     d.act, d.act_a, d.act_b = L.act, L.act_a, L.act_b
     d.src_dtype, d.dst_dtype = (DT_F16 if half else DT_F32), _dt(out)
     with torch.cuda.device(x0.device):
-        if residual is None:
-            _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
-        else:
-            assert residual.shape == out.shape and residual.dtype == out.dtype and residual.is_contiguous() and residual.is_cuda
-            _lib.check(lib.mr_conv2d_nhwc_tc_res(ctypes.byref(d), residual.data_ptr(), n_pad, k_pad, int(round_out), _stream(x0)),
-                       "mr_conv2d_nhwc_tc_res")
+        _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
     return out
 
 

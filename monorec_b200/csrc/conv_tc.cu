@@ -15,8 +15,8 @@
 // Pipelines: smem full/empty mbarrier ring between TMA and MMA; tmem full/empty mbarriers between MMA and epilogue (the
 // accumulator is double-buffered in TMEM, the kernel is persistent over output tiles).
 // Variants chosen by the host code at the bottom of this file: 64-byte swizzle rows for half sources of <= 32 channels;
-// epilogue stores transposed across lane quads (full 32-byte sectors); conv_tc_halo_kernel (resident weights, one input
-// box per tile) for stride-1 layers whose weights fit in shared memory twice per SM.
+// conv_tc_halo_kernel (resident weights, one input box per tile) for stride-1 layers whose weights fit in shared memory
+// twice per SM.  The epilogue is staged through shared memory (8 pixels x 64 contiguous bytes per store instruction).
 //
 // Reference being replaced: nn.Conv2d / nn.ConvTranspose2d + bias + LeakyReLU of model/layers.py:289-400 as used by
 // MaskModule / DepthModule (model/monorec/monorec_model.py:287-385, :476-557).
@@ -47,10 +47,8 @@ struct TcArgs {
     int kc;                        // channels per K chunk: 32 (fp32 sources, kind::tf32) or 64 (half sources, kind::f16)
     int f16, out_f16;              // half sources+weights / half destination
     uint32_t idesc;                // UMMA instruction descriptor
-    int quad;                      // 1: quad-transposed epilogue stores (64 contiguous bytes per pixel per store instruction)
     int row_bytes;                 // bytes of one K chunk row in shared memory = swizzle span: 128, or 64 (half sources, 32-channel chunks)
     uint64_t desc_hi;              // smem descriptor without the start address (LBO, SBO = 8 rows, version, swizzle mode)
-    const void* residual;          // staged epilogue only: tensor laid out like dst, added before the activation (or null)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -183,95 +181,14 @@ __device__ __forceinline__ void epilogue_row(uint32_t trow, const TcArgs& a, con
     }
 }
 
-__device__ __forceinline__ uint4 shfl_xor_u4(uint4 v, int m) {
-    v.x = __shfl_xor_sync(0xffffffffu, v.x, m);
-    v.y = __shfl_xor_sync(0xffffffffu, v.y, m);
-    v.z = __shfl_xor_sync(0xffffffffu, v.z, m);
-    v.w = __shfl_xor_sync(0xffffffffu, v.w, m);
-    return v;
-}
-// 4x4 transpose of 16-byte elements over the 4 lanes of a quad.  In: e[c] = chunk c of this lane's pixel.
-// Out: e[k] = chunk (lane & 3) of the pixel owned by lane k of the quad.
-__device__ __forceinline__ void quad_transpose(uint4 (&e)[4], int lane) {
-    const bool b0 = lane & 1, b1 = lane & 2;
-#pragma unroll
-    for (int j = 0; j < 4; j += 2) {
-        const uint4 recv = shfl_xor_u4(b0 ? e[j] : e[j + 1], 1);
-        if (b0) e[j] = recv; else e[j + 1] = recv;
-    }
-    const uint4 r0 = shfl_xor_u4(b1 ? e[0] : e[2], 2), r1 = shfl_xor_u4(b1 ? e[1] : e[3], 2);
-    if (b1) { e[0] = r0; e[1] = r1; } else { e[2] = r0; e[3] = r1; }
-}
-
-__device__ __forceinline__ float finish(float x, const TcArgs& a) {
-    if (a.act == MR_ACT_LEAKY) x = fmaxf(x, a.act_a * x);          // slope in (0, 1)
-    else if (a.act != MR_ACT_NONE) x = act_fn(x, a.act, a.act_a, a.act_b);
-    if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-    return x;
-}
-
-// Same results as epilogue_row, different store pattern: the accumulator layout gives every thread one pixel, so a plain
-// 16-byte store per thread touches 32 different pixels (half a 32-byte sector each).  Here the 4 lanes of a quad (4 adjacent
-// pixels of one output row) first transpose 4 x 16-byte chunks through shuffles, so that each store instruction writes 64
-// contiguous bytes per pixel: full sectors, a quarter of the lines per instruction.  Needs 16-byte aligned channel slices
-// and Cout a multiple of the chunk (4 floats / 8 halves); all 32 lanes must call it (shuffles), stores are predicated.
-__device__ __forceinline__ void epilogue_row_quad(uint32_t trow, const TcArgs& a, const float* bias_s, float* op, bool row_live,
-                                                  int ox, int lane) {
-    const int l = lane & 3;
-    const long pstride = (long)a.dst_c * a.ox_step;    // elements between horizontally adjacent output pixels
-    for (int n0 = 0; n0 < a.n_pad; n0 += 32) {
-        uint32_t r0[16], r1[16];
-        const bool second = n0 + 16 < a.n_pad;
-        tmem_ld16_nowait(trow + (uint32_t)n0, r0);
-        if (second) tmem_ld16_nowait(trow + (uint32_t)(n0 + 16), r1);
-        tmem_ld_wait();
-        if (a.out_f16) {
-            uint4 e[4];
-            __half2* h = reinterpret_cast<__half2*>(e);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                h[j] = __floats2half2_rn(finish(__uint_as_float(r0[2 * j]) + bias_s[n0 + 2 * j], a),
-                                         finish(__uint_as_float(r0[2 * j + 1]) + bias_s[n0 + 2 * j + 1], a));
-                h[8 + j] = second ? __floats2half2_rn(finish(__uint_as_float(r1[2 * j]) + bias_s[n0 + 16 + 2 * j], a),
-                                                      finish(__uint_as_float(r1[2 * j + 1]) + bias_s[n0 + 17 + 2 * j], a))
-                                  : __floats2half2_rn(0.f, 0.f);
-            }
-            quad_transpose(e, lane);
-            const int col = n0 + 8 * l;
-            __half* base = reinterpret_cast<__half*>(op) + col;
-            const bool col_ok = row_live && (col + 8 <= a.Cout);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (col_ok && (ox - l + k) < a.Wo) *reinterpret_cast<uint4*>(base + (long)(k - l) * pstride) = e[k];
-        } else {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                if (hh == 1 && !second) break;
-                const int nb = n0 + 16 * hh;
-                uint4 e[4];
-                uint32_t* w = reinterpret_cast<uint32_t*>(e);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) w[j] = __float_as_uint(finish(__uint_as_float(hh ? r1[j] : r0[j]) + bias_s[nb + j], a));
-                quad_transpose(e, lane);
-                const int col = nb + 4 * l;
-                float* base = op + col;
-                const bool col_ok = row_live && (col + 4 <= a.Cout);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (col_ok && (ox - l + k) < a.Wo) *reinterpret_cast<uint4*>(base + (long)(k - l) * pstride) = e[k];
-            }
-        }
-    }
-}
-
 // out-of-line copy of the generic epilogue for the staged kernel's rare fallback (keeps its hot code small)
 // (`a` by value: a reference would force the kernel's parameter block onto the local stack for the hot path as well)
 __device__ __noinline__ void epilogue_row_outofline(uint32_t trow, const TcArgs a, const float* bias_s, float* op, bool live, bool vec_ok) {
     epilogue_row(trow, a, bias_s, op, live, vec_ok);
 }
 
-// ---- staged epilogue (conv_tc_kernel<1>, opt-in until measured: MONOREC_B200_TC_EPI=1) -----------------------------------------
-// The source-level profile of the default epilogue (profiles/r01_k2_fullres_f16_quad_ncu_details.txt and the source page of
+// ---- staged epilogue -----------------------------------------------------------------------------------------------------------
+// The source-level profile of round 1's register epilogue (profiles/r01_k2_fullres_f16_quad_ncu_details.txt and the source page of
 // the same capture) shows ~900 executed instructions per warp and tile spread over a 12 700-instruction kernel body
 // (23 % of the stall samples are instruction-fetch misses) -- per-element activation switches, predicates and 48 SEL + 16
 // SHFL per quad transpose.  This variant keeps the per-tile decisions out of the element loop (LeakyReLU as max(x, slope*x)
@@ -344,71 +261,6 @@ __device__ __forceinline__ void epilogue_staged(uint32_t trow, const TcArgs& a, 
     }
 }
 
-// Residual variant of the staged epilogue (ResNet basic blocks): out = act(acc + bias + residual), residual laid out and
-// typed like the destination.  The pre-activation sums are staged in fp32 (16 channels = 64 bytes per pixel and step); the
-// lane that stores chunk c of pixel q also loads the matching residual chunk, so both accesses are coalesced.
-template <bool OUT_F16>
-__device__ __forceinline__ void epilogue_staged_res(uint32_t trow, const TcArgs& a, const float* bias_s, uint32_t stg, uint8_t* const (&qptr)[4],
-                                                    const bool (&qlive)[4], int lane, float slope) {
-    const uint32_t wrow = stg + (uint32_t)lane * 64u;
-    const uint32_t wsw = ((uint32_t)lane >> 1) & 3u;
-    const uint32_t c = (uint32_t)lane & 3u;
-    const ptrdiff_t rdelta = reinterpret_cast<const uint8_t*>(a.residual) - reinterpret_cast<const uint8_t*>(a.dst);
-    uint32_t raddr[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t q = ((uint32_t)lane >> 2) + 8u * k;
-        raddr[k] = stg + q * 64u + ((c ^ ((q >> 1) & 3u)) << 4);
-    }
-    for (int n0 = 0; n0 < a.n_pad; n0 += 16) {
-        uint32_t r0[16];
-        tmem_ld16_nowait(trow + (uint32_t)n0, r0);
-        tmem_ld_wait();
-#pragma unroll
-        for (uint32_t cc = 0; cc < 4; ++cc) {
-            const float x0 = __uint_as_float(r0[4 * cc]) + bias_s[n0 + 4 * cc], x1 = __uint_as_float(r0[4 * cc + 1]) + bias_s[n0 + 4 * cc + 1];
-            const float x2 = __uint_as_float(r0[4 * cc + 2]) + bias_s[n0 + 4 * cc + 2], x3 = __uint_as_float(r0[4 * cc + 3]) + bias_s[n0 + 4 * cc + 3];
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wrow + ((cc ^ wsw) << 4)), "r"(__float_as_uint(x0)),
-                         "r"(__float_as_uint(x1)), "r"(__float_as_uint(x2)), "r"(__float_as_uint(x3))
-                         : "memory");
-        }
-        __syncwarp();
-        const bool col_ok = n0 + (int)c * 4 + 4 <= a.Cout;
-        const size_t boff = ((size_t)n0 + (size_t)c * 4) * (OUT_F16 ? 2 : 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint4 v;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(raddr[k]) : "memory");
-            if (qlive[k] && col_ok) {
-                uint8_t* o = qptr[k] + boff;
-                float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
-                if (OUT_F16) {
-                    const uint2 rr = *reinterpret_cast<const uint2*>(o + rdelta);
-                    const float2 ra = __half22float2(*reinterpret_cast<const __half2*>(&rr.x)), rb = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
-                    x[0] += ra.x; x[1] += ra.y; x[2] += rb.x; x[3] += rb.y;
-                } else {
-                    const float4 rr = *reinterpret_cast<const float4*>(o + rdelta);
-                    x[0] += rr.x; x[1] += rr.y; x[2] += rr.z; x[3] += rr.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    x[j] = fmaxf(x[j], slope * x[j]);
-                    if (a.round_out) x[j] = __uint_as_float((__float_as_uint(x[j]) + 0x1000u) & 0xFFFFE000u);
-                }
-                if (OUT_F16) {
-                    uint2 ov;
-                    *reinterpret_cast<__half2*>(&ov.x) = __floats2half2_rn(x[0], x[1]);
-                    *reinterpret_cast<__half2*>(&ov.y) = __floats2half2_rn(x[2], x[3]);
-                    *reinterpret_cast<uint2*>(o) = ov;
-                } else {
-                    *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-                }
-            }
-        }
-        __syncwarp();
-    }
-}
-
 // One tile of the staged epilogue for a warp (TMEM lane quadrant q): output pointers / liveness of the 4 pixels each lane
 // stores for, then the 64-byte steps; tiles are kTW x kTH pixels with accumulator row p = y * kTW + x.  Layers the staged
 // path cannot take (unaligned channel slices, the rare activations) go through the generic out-of-line epilogue.
@@ -428,10 +280,7 @@ __device__ __forceinline__ void staged_tile(const TcArgs& a, const float* bias_s
                                     a.dst_c + a.dst_coff;
             qptr[k] = reinterpret_cast<uint8_t*>(a.dst) + qidx * esize;
         }
-        if (a.residual != nullptr) {
-            if (a.out_f16) epilogue_staged_res<true>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
-            else epilogue_staged_res<false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
-        } else if (a.out_f16) epilogue_staged<true, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
+        if (a.out_f16) epilogue_staged<true, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
         else if (a.round_out) epilogue_staged<false, true>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
         else epilogue_staged<false, false>(trow, a, bias_s, stg, qptr, qlive, lane, slope);
     } else {
@@ -451,7 +300,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent: each CTA loops over output tiles (tile = blockIdx.x, += gridDim.x).  The TMA->MMA shared-memory ring keeps
 // flowing across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the
 // main loop of tile i+1.
-template <int EPI>   // 0: register epilogues (default), 1: staged epilogue above
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -551,7 +399,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 __syncwarp();
             }
         }
-    } else if constexpr (EPI == 1) {
+    } else {
         // ===================== epilogue, staged through shared memory (see epilogue_staged) =====================
         __shared__ __align__(16) uint8_t stage_s[4][2048];
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read (the 4 epilogue warps have distinct ones)
@@ -569,32 +417,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
             staged_tile<kTileW, kTileH>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-        }
-    } else {
-        // ===================== epilogue: TMEM -> registers -> bias/activation -> NHWC =====================
-        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-        const int p = 32 * q + lane;            // pixel (= accumulator row) of this thread
-        const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
-        const bool quad_ok = vec_ok && a.quad && (a.Cout & (a.out_f16 ? 7 : 3)) == 0;
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
-            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
-            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
-            const int oy = tile_y * kTileH + (p >> 4), ox = tile_x * kTileW + (p & 15);
-            const bool live = (oy < a.Ho) && (ox < a.Wo);
-            const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
-                                    a.dst_c + a.dst_coff;
-            float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
-            const int buf = lt & 1;
-            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            if (quad_ok) epilogue_row_quad(trow, a, bias_s, op, oy < a.Ho, ox, lane);
-            else epilogue_row(trow, a, bias_s, op, live, vec_ok);
-            // hand the accumulator buffer back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -630,15 +452,13 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_
            ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
 }
 
-// ROWB: bytes per shared-memory row, 128 (default) or 64 (opt-in, half sources of <= 32 channels); EPI: 0 register epilogues
-// (default), 1 staged epilogue (opt-in); GROUPS: groups of 4 epilogue warps (1 default; 2 = 8 epilogue warps over 4 TMEM
-// accumulators, opt-in, for the layers that only fit one CTA per SM)
-template <int ROWB, int EPI, int GROUPS>
-__global__ void __launch_bounds__(kTcThreads + 128 * (GROUPS - 1))
+// ROWB: bytes per shared-memory row, 128 or 64 (half sources of <= 32 channels)
+template <int ROWB>
+__global__ void __launch_bounds__(kTcThreads)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int kBufs = 2 * GROUPS;                            // TMEM accumulators: two per epilogue group
+    constexpr int kBufs = 2;                                     // TMEM accumulators (double-buffered)
     __shared__ __align__(8) uint64_t bars[2 * 4 + 2 * kBufs + 1];   // afull[4], aempty[4], tmem_full[kBufs], tmem_empty[kBufs], bfull
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[256];
@@ -711,7 +531,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         int it = 0, lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int buf = lt & (kBufs - 1);
-            mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> (GROUPS == 1 ? 1 : 2)) & 1u) ^ 1u);
+            mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_d + (uint32_t)(buf * a.n_pad);
             for (int cg = 0; cg < chunks_per_tap; ++cg, ++it) {
@@ -739,12 +559,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 __syncwarp();
             }
         }
-    } else if constexpr (EPI == 1) {
+    } else {
         // ===================== epilogue, staged through shared memory (tile = 16 rows x 8 columns) =====================
-        static_assert(GROUPS == 1 || GROUPS == 2, "one or two groups of four epilogue warps");
-        __shared__ __align__(16) uint8_t stage_s[4 * GROUPS][2048];
+        __shared__ __align__(16) uint8_t stage_s[4][2048];
         const int q = warp & 3;                 // TMEM lane quadrant
-        const int g = (warp - 2) >> 2;          // epilogue group: takes the tiles with lt % GROUPS == g
         const uint32_t stg = smem_u32(&stage_s[warp - 2][0]);
         const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
         const bool lean_ok = vec_ok && (a.Cout & (a.out_f16 ? 7 : 3)) == 0 && !(a.out_f16 && a.round_out) &&
@@ -752,39 +570,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const float slope = a.act == MR_ACT_LEAKY ? a.act_a : 1.0f;
         int lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
-            if (GROUPS > 1 && (lt & (GROUPS - 1)) != g) continue;
             const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
             const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
             const int buf = lt & (kBufs - 1);
-            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> (GROUPS == 1 ? 1 : 2)) & 1u);
+            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
             staged_tile<8, 16>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-        }
-    } else {
-        // ===================== epilogue (tile = 16 rows x 8 columns) =====================
-        const int q = warp & 3;
-        const int p = 32 * q + lane;
-        const bool vec_ok = ((a.dst_c | a.dst_coff) & (a.out_f16 ? 7 : 3)) == 0;
-        const bool quad_ok = vec_ok && a.quad && (a.Cout & (a.out_f16 ? 7 : 3)) == 0;
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
-            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
-            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
-            const int oy = tile_y * 16 + (p >> 3), ox = tile_x * 8 + (p & 7);
-            const bool live = (oy < a.Ho) && (ox < a.Wo);
-            const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
-                                    a.dst_c + a.dst_coff;
-            float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
-            const int buf = lt & (kBufs - 1);
-            mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> (GROUPS == 1 ? 1 : 2)) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            if (quad_ok) epilogue_row_quad(trow, a, bias_s, op, oy < a.Ho, ox, lane);
-            else epilogue_row(trow, a, bias_s, op, live, vec_ok);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -817,7 +609,7 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, int n_pad, int k_pad, int round_out, void* stream) {
+static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream) {
     MR_REQUIRE(desc != nullptr, "mr_conv2d_nhwc_tc: null descriptor");
     const mr_conv_desc& d = *desc;
     MR_REQUIRE(d.n_src >= 1 && d.n_src <= MR_CONV_MAX_SRC, "mr_conv2d_nhwc_tc: n_src=%d out of range", d.n_src);
@@ -857,8 +649,6 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, i
     a.kc = kc; a.f16 = f16 ? 1 : 0; a.out_f16 = (d.dst_dtype == MR_DT_F16) ? 1 : 0;
     // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6); a/b format @[7,10)/[10,13): TF32 = 2,
     // F16 = 0; K-major A and B; N >> 3 @[17,23); M >> 4 @[24,29)
-    static const bool kQuad = getenv("MONOREC_B200_TC_QUAD") ? (atoi(getenv("MONOREC_B200_TC_QUAD")) != 0) : true;   // epilogue store pattern
-    a.quad = kQuad ? 1 : 0;
     a.idesc = (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n_pad >> 3) << 17) | ((128u >> 4) << 24);
     int ksum = 0;
     // "halo" variant (one input box per tile, resident weights): stride 1, taps reach at most 8 px to the right, weights fit
@@ -870,37 +660,23 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, i
     // SM (32->32 3x3 over the single-frame volumes: 631 -> 452 us in TF32, 489 -> 429 us in half); with a single CTA per SM
     // its four epilogue warps become the bottleneck (48->48 3x3: 300 -> 335 us), so those layers keep the tap-refetch kernel.
     static const int halo_env = getenv("MONOREC_B200_TC_HALO") ? atoi(getenv("MONOREC_B200_TC_HALO")) : -1;
-    // experimental staged epilogue (conv_tc_kernel<1>, conv_tc_halo_kernel<.,1>): 8 KB of static shared memory per CTA more
-    static const bool kStagedEpi = getenv("MONOREC_B200_TC_EPI") ? (atoi(getenv("MONOREC_B200_TC_EPI")) == 1) : false;
     static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : true;
-    // 64-byte rows inside the halo box (half sources of <= 32 channels packed with 32-channel chunks): not yet measured on the
-    // GPU, therefore opt-in; the Python side packs such layers with 64-channel chunks unless this is set
-    static const bool halo_k32 = getenv("MONOREC_B200_TC_HALO_K32") ? (atoi(getenv("MONOREC_B200_TC_HALO_K32")) != 0) : false;
+    // (64-byte rows are fine inside the halo box too: half sources of <= 32 channels packed with 32-channel chunks; measured
+    // 429 -> 203 us on the 32->32 3x3 layer over the single-frame volumes, profiles/r02_k2_variants.txt)
     const size_t halo_a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * a.row_bytes;
     const size_t bres_al = (bres + 1023) & ~size_t(1023);
     auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights (228 KB per SM, 1 KB reserved + ~1.1 KB static per CTA)
-        const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas - (kStagedEpi ? 8 * 1024 : 0);
+        const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas - 8 * 1024;   // 8 KB: the epilogue's staging buffers (static)
         int st = bres_al + 2048 < budget ? (int)((budget - 2048 - bres_al) / halo_a_bytes) : 0;
         return st > 4 ? 4 : st;
     };
-    // 8 epilogue warps + 4 accumulators in a single CTA per SM for the layers that do not fit twice (needs the staged epilogue)
-    static const bool halo_epi8 = getenv("MONOREC_B200_TC_HALO_EPI8") ? (atoi(getenv("MONOREC_B200_TC_HALO_EPI8")) != 0) : false;
-    int halo_ctas = 0, halo_groups = 1;
-    if (halo_env != 0 && (!f16 || halo_f16) && (a.row_bytes == 128 || halo_k32) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
+    int halo_ctas = 0;
+    if (halo_env != 0 && (!f16 || halo_f16) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
         if (halo_env == 1 || halo_env == 2) halo_ctas = halo_fit(halo_env) >= 2 ? halo_env : 0;
         else if (halo_fit(2) >= 2) halo_ctas = 2;
-        else if (halo_epi8 && kStagedEpi && 4 * n_pad <= 512 && d.kh * d.kw >= 3) {
-            // one CTA per SM: weights + >= 2 input stages + 16 KB of staging
-            const size_t budget1 = (size_t)200 * 1024;
-            if (bres_al + 2048 + 2 * halo_a_bytes <= budget1) { halo_ctas = 1; halo_groups = 2; }
-        }
     }
     const bool halo = halo_ctas > 0;
-    int halo_stages = halo ? halo_fit(halo_ctas) : 0;
-    if (halo_groups == 2) {   // halo_fit(1) reserves 8 KB of staging; the 8-warp variant needs 16
-        halo_stages = (int)(((size_t)200 * 1024 - 2048 - bres_al) / halo_a_bytes);
-        if (halo_stages > 4) halo_stages = 4;
-    }
+    const int halo_stages = halo ? halo_fit(halo_ctas) : 0;
     CUtensorMap tmA[MR_CONV_MAX_SRC];
     for (int s = 0; s < d.n_src; ++s) {
         const int C = d.src_c[s];
@@ -960,7 +736,7 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, i
     int ctas_per_sm = (int)(512 / cols_needed);
     if (ctas_per_sm > 4) ctas_per_sm = 4;
     if (kForceCtas > 0 && (uint32_t)kForceCtas * cols_needed <= 512) ctas_per_sm = kForceCtas;
-    const size_t budget = (size_t)(200 * 1024) / ctas_per_sm - (kStagedEpi ? 8 * 1024 : 0);
+    const size_t budget = (size_t)(200 * 1024) / ctas_per_sm - 8 * 1024;
     int stages = (int)(budget / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -972,14 +748,6 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, i
     a.dst_H = d.dst_H; a.dst_W = d.dst_W; a.dst_c = d.dst_c; a.dst_coff = d.dst_coff;
     a.oy_step = d.oy_step; a.ox_step = d.ox_step; a.oy_off = d.oy_off; a.ox_off = d.ox_off;
     a.act = d.act; a.act_a = d.act_a; a.act_b = d.act_b; a.round_out = round_out;
-    a.residual = residual;
-    if (residual != nullptr) {
-        const int vm = a.out_f16 ? 7 : 3;
-        MR_REQUIRE(kStagedEpi, "mr_conv2d_nhwc_tc: a residual input needs the staged epilogue (MONOREC_B200_TC_EPI=1)");
-        MR_REQUIRE(((d.dst_c | d.dst_coff | d.Cout) & vm) == 0 && !(a.out_f16 && round_out) && (d.act == MR_ACT_NONE || d.act == MR_ACT_LEAKY) &&
-                       (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
-                   "mr_conv2d_nhwc_tc: residual epilogue needs 16-byte aligned channel slices and a none/leaky activation");
-    }
     if (halo) {
         a.stages = halo_stages;
         const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
@@ -990,18 +758,7 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, i
             kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
             return MR_OK;
         };
-        int lrc;
-        if (halo_groups == 2) {          // 8 epilogue warps, 4 accumulators (opt-in, staged epilogue only)
-            uint32_t cols4 = 32;
-            while (cols4 < (uint32_t)(4 * n_pad)) cols4 <<= 1;
-            a.tmem_cols = cols4;
-            lrc = a.row_bytes == 128 ? launch_halo(conv_tc_halo_kernel<128, 1, 2>, kTcThreads + 128)
-                                     : launch_halo(conv_tc_halo_kernel<64, 1, 2>, kTcThreads + 128);
-        } else if (a.row_bytes == 128) {
-            lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<128, 1, 1>, kTcThreads) : launch_halo(conv_tc_halo_kernel<128, 0, 1>, kTcThreads);
-        } else {
-            lrc = kStagedEpi ? launch_halo(conv_tc_halo_kernel<64, 1, 1>, kTcThreads) : launch_halo(conv_tc_halo_kernel<64, 0, 1>, kTcThreads);
-        }
+        const int lrc = a.row_bytes == 128 ? launch_halo(conv_tc_halo_kernel<128>, kTcThreads) : launch_halo(conv_tc_halo_kernel<64>, kTcThreads);
         if (lrc != MR_OK) return lrc;
         MR_LAUNCH_CHECK("conv_tc_halo_kernel");
         return MR_OK;
@@ -1009,22 +766,12 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, const void* residual, i
     const size_t smem = (size_t)stages * stage_bytes + 1024;
     int grid = sms * ctas_per_sm;
     if (grid > a.total_tiles) grid = a.total_tiles;
-    if (kStagedEpi) {
-        MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(212 * 1024)));
-        conv_tc_kernel<1><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
-    } else {
-        MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-        conv_tc_kernel<0><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
-    }
+    MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(212 * 1024)));
+    conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
     MR_LAUNCH_CHECK("conv_tc_kernel");
     return MR_OK;
 }
 
 extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream) {
-    return conv2d_nhwc_tc_impl(desc, nullptr, n_pad, k_pad, round_out, stream);
-}
-
-extern "C" int mr_conv2d_nhwc_tc_res(const mr_conv_desc* desc, const void* residual, int n_pad, int k_pad, int round_out, void* stream) {
-    MR_REQUIRE(residual != nullptr, "mr_conv2d_nhwc_tc_res: null residual");
-    return conv2d_nhwc_tc_impl(desc, residual, n_pad, k_pad, round_out, stream);
+    return conv2d_nhwc_tc_impl(desc, n_pad, k_pad, round_out, stream);
 }

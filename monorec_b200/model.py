@@ -5,8 +5,8 @@ Same constructor keywords, same `forward(data_dict) -> data_dict` contract and d
 `state_dict()` keys and shapes, so a reference checkpoint loads unchanged.  The modules below only
 *hold* parameters in the reference's layout; the arithmetic runs in libmonorec_b200.so (fused cost-volume kernel +
 convolution engine) through the C ABI.  The ResNet-18 trunk stays on torchvision/cuDNN (third-party arithmetic in the
-reference too; SURVEY.md §8f "next" row 1) with its eval-mode BatchNorms folded; MONOREC_B200_TRUNK=engine (experimental)
-runs it on the conv engine instead.
+reference too; SURVEY.md §8f "next" row 1) with its eval-mode BatchNorms folded, in half precision in half mode.  (Round 2
+measured the trunk on the conv engine at 1.03 ms against cuDNN's 0.71 ms in half mode, so that variant was removed.)
 """
 import os
 
@@ -18,13 +18,9 @@ from .cost_volume import CostVolumeModule
 
 __all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "ResnetEncoder"]
 
-# experimental: ResNet trunk on the conv engine; needs the staged epilogue of the tensor-core kernels for the residual adds
-TRUNK_ENGINE = os.environ.get("MONOREC_B200_TRUNK", "cudnn").lower() == "engine"
-# experimental: in half mode run the cuDNN trunk in half as well (folded weights and activations), so that its NHWC outputs feed
-# the conv engine without casts
-TRUNK_CUDNN_F16 = os.environ.get("MONOREC_B200_TRUNK", "cudnn").lower() == "cudnn_f16"
-if TRUNK_ENGINE and os.environ.get("MONOREC_B200_TC_EPI", "0") != "1":
-    raise RuntimeError("MONOREC_B200_TRUNK=engine needs MONOREC_B200_TC_EPI=1 (residual adds live in the staged epilogue)")
+# in half mode the cuDNN trunk runs in half as well (folded weights and activations): its NHWC outputs feed the conv engine
+# without casts (0.82 -> 0.71 ms at B=8); MONOREC_B200_TRUNK=cudnn_f32 keeps it in fp32
+TRUNK_CUDNN_F16 = os.environ.get("MONOREC_B200_TRUNK", "cudnn_f16").lower() != "cudnn_f32"
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -159,76 +155,9 @@ class ResnetEncoder(nn.Module):
             self.features.append(x)
         return self.features
 
-    # ---- experimental: the same trunk on the conv engine, NHWC, folded BatchNorm, ReLU as a
-    #      LeakyReLU of slope 0, residual adds in the epilogue of each block's second convolution.  Opt-in
-    #      (MONOREC_B200_TRUNK=engine) and only with the staged epilogue (MONOREC_B200_TC_EPI=1), which implements the
-    #      residual input; not yet measured on the GPU.
-    def _engine_layers(self):
-        f = self._folded()
-        sig = (C.MODE, getattr(self, "_fold_sig", None))
-        if getattr(self, "_engine_sig", None) == sig:
-            return self._engine_cache
-        half = C.MODE == "f16"
-        cpad = 8 if half else 4              # NHWC pixel stride of the 3-channel input must be a multiple of 16 bytes
-
-        def relu_conv(w, b, cin, stride=(1, 1), pad=(1, 1), relu=True):
-            # <= 256 output channels per launch (UMMA N); wider layers are split into channel slices of the same output
-            parts = []
-            for c0 in range(0, w.shape[0], 256):
-                parts.append((c0, C.PackedConv(w[c0:c0 + 256], b[c0:c0 + 256], (cin,), stride=stride, pad=pad,
-                                               act=C.ACT_LEAKY if relu else C.ACT_NONE, act_a=0.0)))
-            return parts
-        with torch.no_grad():
-            w1, b1 = f["stem"]
-            w1 = torch.cat([w1, w1.new_zeros(w1.shape[0], cpad - 3, w1.shape[2], w1.shape[3])], 1)
-            layers = {"cpad": cpad, "stem": relu_conv(w1, b1, cpad, stride=(2, 2), pad=(3, 3)), "blocks": []}
-            for blocks in f["blocks"]:
-                out = []
-                for (wa, ba), stride, (wb, bb), down in blocks:
-                    cin, cout = wa.shape[1], wa.shape[0]
-                    out.append({"conv1": relu_conv(wa, ba, cin, stride=tuple(stride), pad=(1, 1)),
-                                "conv2": relu_conv(wb, bb, cout, pad=(1, 1)),     # ReLU after the residual add
-                                "down": None if down is None else relu_conv(down[0], down[1], cin, stride=tuple(down[2]), pad=(0, 0),
-                                                                            relu=False),
-                                "cout": cout})
-                layers["blocks"].append(out)
-        self._engine_cache, self._engine_sig = layers, sig
-        return layers
-
-    @staticmethod
-    def _run_parts(parts, x, cout, residual=None):
-        out = None
-        for c0, layer in parts:
-            if out is None:
-                B, Hs, Ws, _ = x.shape
-                sy, sx = layer.stride
-                out = torch.empty(B, -(-Hs // sy), -(-Ws // sx), cout, device=x.device, dtype=C.act_dtype())
-            layer([x], out=out, out_coff=c0, residual=residual)
-        return out
-
-    def _forward_engine(self, input_image):
-        L = self._engine_layers()
-        x = (input_image - 0.45) / 0.225
-        B, _, H, W = x.shape
-        xin = torch.zeros(B, H, W, L["cpad"], device=x.device, dtype=C.act_dtype())
-        C.nchw_to_nhwc(x.to(torch.float32), out=xin, out_coff=0)
-        x = self._run_parts(L["stem"], xin, 64)
-        feats = [x]
-        x = C.maxpool3s2(x)
-        for blocks in L["blocks"]:
-            for blk in blocks:
-                idt = x if blk["down"] is None else self._run_parts(blk["down"], x, blk["cout"])
-                y = self._run_parts(blk["conv1"], x, blk["cout"])
-                x = self._run_parts(blk["conv2"], y, blk["cout"], residual=idt)
-            feats.append(x)
-        self.features = [t.permute(0, 3, 1, 2) for t in feats]     # logical (B,C,H,W) views of the NHWC tensors
-        return self.features
-
     def forward(self, input_image):
         e = self.encoder
         if not e.training and not torch.is_grad_enabled():
-            if TRUNK_ENGINE and input_image.is_cuda:
-                return self._forward_engine(input_image)
             return self._forward_folded(input_image)
         x = (input_image - 0.45) / 0.225
         self.features = [e.relu(e.bn1(e.conv1(x)))]

@@ -18,6 +18,8 @@ Files written
   model_kitti_sample.npz  full MonoRecModel forward on the bundled KITTI sample, seeded weights (`--only-kitti-model`)
   model_synth_small.npz   full MonoRecModel forward (seeded weights, 2 gains) on a small synthetic config:
                           cv_mask, 4 depth maps, image_features checksums
+  model_fp64.npz          the same two model configurations evaluated by the reference in float64 (`--only-model-fp64`):
+                          the reference's own fp32 rounding noise on `result` / `cv_mask`, which sizes the GPU gates
 """
 import os
 import sys
@@ -162,6 +164,34 @@ def main():
                   "mask range", float(r["cv_mask"].min()), float(r["cv_mask"].max()))
         out["wseed"] = np.array([7])
         np.savez_compressed(HERE / "model_kitti_sample.npz", **out)
+        return
+    if "--only-model-fp64" in sys.argv:
+        # The reference's OWN fp32 rounding noise on the gated quantities: the same model and inputs evaluated in float64.
+        # |result32 - result64| is what any fp32 implementation can be told apart from another by; the GPU tests gate the
+        # drop-in at max(1e-3, 4 x that) (tests/test_convnet_gpu.py).  Written to a separate small file.
+        to64 = lambda d: {k: ([t.double() for t in v] if isinstance(v, list) else v.double()) for k, v in d.items()}
+        out = {}
+        s = load_kitti_sample()
+        for cfg, data in (("kitti", sample_to_dict(s)), ("synth", make_inputs(1, 2, 64, 128, seed=5))):
+            for gain_tag, gain in (("g1", 1.0), ("g07", 0.7)):
+                model = ref_mod.MonoRecModel()
+                model.load_state_dict(seeded_state_dict(model, seed=7, gain=gain))
+                model.eval()
+                with torch.no_grad():
+                    r32 = model(dict(data))
+                    torch.set_default_dtype(torch.float64)      # the reference creates its grids / patch kernel with the default dtype
+                    model64 = ref_mod.MonoRecModel()
+                    model64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in model.state_dict().items()})
+                    r64 = model64.eval()(to64(data))
+                    torch.set_default_dtype(torch.float32)
+                d_res = (r32["result"].double() - r64["result"]).abs().max().item()
+                d_mask = (r32["cv_mask"].double() - r64["cv_mask"]).abs().max().item()
+                d_heads = [(a.double() - b).abs().max().item() for a, b in zip(r32["predicted_inverse_depths"], r64["predicted_inverse_depths"])]
+                out[f"{cfg}_{gain_tag}_noise"] = np.array([d_res, d_mask] + d_heads)
+                out[f"{cfg}_{gain_tag}_result64"] = r64["result"].float().numpy()
+                out[f"{cfg}_{gain_tag}_cv_mask64"] = r64["cv_mask"].float().numpy().astype(np.float16)
+                print(cfg, gain_tag, "reference fp32 vs fp64: result", d_res, "mask", d_mask, "heads", d_heads, flush=True)
+        np.savez_compressed(HERE / "model_fp64.npz", **out)
         return
     if "--only-d64f6" in sys.argv:
         # BASELINE config 5's plane and frame counts (64 planes, 6 source frames) at a small size; added after the other

@@ -112,13 +112,16 @@ def test_full_model_matches_reference_golden(gain_tag, gain, conv_mode):
     dm = np.abs(out["cv_mask"].cpu().numpy() - g[f"{gain_tag}_cv_mask"]).max()
     dd = [np.abs(p.cpu().numpy() - g[f"{gain_tag}_depth{i}"]).max() for i, p in enumerate(out["predicted_inverse_depths"])]
     print(conv_mode, gain_tag, "mask max|d|", dm, "depth max|d|", dd)
-    # g07 keeps the heads in their responsive range and is gated at the north-star 1e-3; the g1 weights amplify the
-    # ~1e-4 fp32 noise of the cost volume (both implementations' and the reference's own) by ~20x through
-    # saturating layers, so that case is a looser end-to-end sanity gate -- the conv stacks themselves are gated at 2e-4
-    # relative on identical inputs in test_modules_match_oracle_per_stage
-    tol = 1e-3 if gain_tag == "g07" else 1e-2
-    if conv_mode == "tf32":
-        tol = 1e-3 if gain_tag == "g07" else 5e-2    # north-star 1e-3 on the responsive case; g1 amplifies TF32 noise
+    # fp32 arithmetic: gated at 1e-4, a tenth of the north-star 1e-3 (measured on B200: 6.7e-6 for g1, 3.4e-7 for g07; the
+    # reference's own fp32-vs-fp64 deviation on this configuration is 1.7e-6 / 1.8e-7, tests/golden/model_fp64.npz).
+    # TF32 arithmetic (10-bit mantissa products in every dense layer) is a documented reduced-precision mode, not the parity
+    # path: the responsive weight set g07 stays below the north-star 1e-3 (measured 2.0e-4); the g1 weights amplify the
+    # product rounding (measured 4.4e-3) and are gated at 1e-2.
+    n_res, n_mask = _ref_noise("synth", gain_tag)
+    if conv_mode == "fp32":
+        tol = max(1e-4, 4 * max(n_res, n_mask))
+    else:
+        tol = 1e-3 if gain_tag == "g07" else 1e-2
     assert dm < tol and max(dd) < tol
     assert out["result"].shape == (B, 1, H, W) and out["mask"] is out["cv_mask"]
     assert set(["cost_volume", "single_frame_cvs", "image_features", "cv_mask", "predicted_inverse_depths", "result",
@@ -368,3 +371,55 @@ def test_full_model_f16_matches_reference_golden(f16_mode):
     dd = [np.abs(p.cpu().numpy() - g[f"g07_depth{i}"]).max() for i, p in enumerate(out["predicted_inverse_depths"])]
     print("f16 g07 mask max|d|", dm, "depth max|d|", dd)
     assert dm < 2e-3 and max(dd) < 1e-3
+
+
+def _ref_noise(cfg, gain_tag):
+    """The reference's own fp32-vs-fp64 deviation on (result, cv_mask) for this configuration (tests/golden/model_fp64.npz,
+    written by `make_golden.py --only-model-fp64`): no fp32 implementation can be held closer to the fp32 reference than that."""
+    from tests.helpers import GOLDEN
+    n = np.load(GOLDEN / "model_fp64.npz")[f"{cfg}_{gain_tag}_noise"]
+    return float(n[0]), float(n[1])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "f16"])
+@pytest.mark.parametrize("gain_tag,gain", [("g1", 1.0), ("g07", 0.7)])
+def test_full_model_on_bundled_sample(mode, gain_tag, gain):
+    """The north-star parity sentence on the CUDA path: full MonoRecModel on the bundled KITTI sample (256x512, 2 source frames)
+    against the unmodified reference (tests/golden/model_kitti_sample.npz, seeded weights).
+
+    fp32 arithmetic (the parity path): |delta inverse depth| < max(1e-4, 4 x the reference's own fp32-vs-fp64 deviation), i.e.
+    ten times tighter than the north-star 1e-3 for the g1 weights (measured on B200: 5.5e-6; reference noise 2.3e-6).  The g07
+    weight set is chaotic on this image -- the reference itself moves by 8.3e-3 between fp32 and fp64 (tests/golden/
+    model_fp64.npz) -- so its max-norm gate is 4 x that and the informative gate is the share of pixels within 1e-3 (measured
+    0.99924 in every mode; max|d| 4.3e-3, inside the reference's own noise).
+    tf32 / f16 are reduced-precision arithmetic modes (10-bit mantissa products): gated at 1e-2 (measured 3.4e-3 / 4.3e-3 for
+    g1) and on the pixel share within 1e-3 (measured 0.961 / 0.947)."""
+    from monorec_b200 import conv as K
+    from monorec_b200.model import MonoRecModel
+    from monorec_b200.synthetic import seeded_state_dict, to_device
+    from tests.helpers import GOLDEN, kitti_sample_dict
+    g = np.load(GOLDEN / "model_kitti_sample.npz")
+    data, _ = kitti_sample_dict()
+    old = K.MODE
+    K.set_mode(mode)
+    try:
+        model = MonoRecModel()
+        model.load_state_dict(seeded_state_dict(model, seed=int(g["wseed"][0]), gain=gain))
+        model = model.to(DEV).eval()
+        with torch.no_grad():
+            out = model(to_device(data, DEV))
+        torch.cuda.synchronize()
+    finally:
+        K.set_mode(old)
+    dr = np.abs(out["result"].float().cpu().numpy() - g[f"{gain_tag}_result"])
+    dmask = np.abs(out["cv_mask"].float().cpu().numpy() - g[f"{gain_tag}_cv_mask"].astype(np.float32))
+    n_res, n_mask = _ref_noise("kitti", gain_tag)
+    share = float((dr < 1e-3).mean())
+    print(f"bundled sample {mode} {gain_tag}: result max|d| {dr.max():.3e} (reference fp32-vs-fp64 {n_res:.1e}), "
+          f"share within 1e-3: {share:.5f}, mask max|d| {dmask.max():.3e} (reference {n_mask:.1e})")
+    if mode == "fp32":
+        assert dr.max() < max(1e-4, 4 * n_res) and share > 0.999
+        assert dmask.max() < max(1e-3, 4 * n_mask)      # the golden mask is stored as half (5e-4 quantisation)
+    else:
+        assert dr.max() < max(1e-2, 4 * n_res) and share > (0.99 if gain_tag == "g07" else 0.9)
+        assert dmask.max() < max(1e-2, 4 * n_mask)

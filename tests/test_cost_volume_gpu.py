@@ -213,3 +213,12 @@ def test_tma_windows_and_global_gather_agree(B, F, H, W):
         assert d.max() <= 5e-5, f"single-frame volumes differ by {d.max().item():.3e} ({int((d > 2e-6).sum())} values > 2e-6)"
     d = (outs[0][0] - outs[1][0]).abs()
     assert d.max() <= 1e-4, f"fused volumes differ by {d.max().item():.3e}"
+
+
+def test_cost_volume_golden_d64_f6():
+    """CUDA cost volume vs the reference's own output for 64 planes x 6 source frames (tests/golden/cv_synth_d64f6.npz,
+    BASELINE config 5's plane and frame counts); the same gates as test_golden_small_full_tensors."""
+    from tests.helpers import compare_volumes, synth_small_dict
+    data, D, ref_cv, ref_sf = synth_small_dict("d")
+    cv, sf = _run(data, steps=D)
+    print(compare_volumes(cv, sf, ref_cv, ref_sf))

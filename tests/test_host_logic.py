@@ -96,8 +96,8 @@ def test_trunk_batchnorm_folding_matches_unfolded_eval():
 
 def test_tc_weight_packing_chunk_widths():
     """Packed tensor-core weights: [taps][n_pad][k_pad], every source padded to whole K chunks; half sources of <= 32
-    channels use 32-channel chunks (64-byte swizzle rows) except on stride-1 layers, which the halo kernel takes with
-    64-channel chunks (the library derives the chunk width from k_pad: include/monorec_b200.h)."""
+    channels use 32-channel chunks (64-byte swizzle rows; the library derives the chunk width from k_pad:
+    include/monorec_b200.h)."""
     from monorec_b200 import conv as C
     w = torch.randn(24, 32, 3, 3)
     wt, n_pad, k_pad = C.pack_tc_weight(w, (32,), half=False)
@@ -113,47 +113,4 @@ def test_tc_weight_packing_chunk_widths():
     assert float(wt[:, :, 32:64].abs().max()) == 0.0
     s1 = C.PackedConv(w, None, (32,), stride=(1, 1))
     s2 = C.PackedConv(w, None, (32,), stride=(2, 1))
-    assert s1.wtc(True)[2] == (64 if (C.HALO_F16 and not C.HALO_K32) else 32) and s2.wtc(True)[2] == (32 if C.K32 else 64)
-
-
-def test_engine_trunk_wiring_matches_folded_trunk(monkeypatch):
-    """The experimental ResNet trunk on the conv engine (MONOREC_B200_TRUNK=engine): block wiring, explicit PyTorch padding,
-    512-channel splits and the residual placement, checked on the CPU by standing torch ops in for the engine's kernels."""
-    import torch.nn.functional as F
-    from monorec_b200 import conv as C, model as M
-    torch.manual_seed(1)
-    enc = M.ResnetEncoder(18, pretrained=False).eval()
-    for m in enc.modules():
-        if isinstance(m, torch.nn.BatchNorm2d):
-            m.running_mean.normal_(0, 0.3)
-            m.running_var.uniform_(0.5, 2.0)
-            m.bias.data.normal_(0, 0.2)
-
-    def run_parts(parts, x, cout, residual=None):
-        xn = x.permute(0, 3, 1, 2)
-        outs = []
-        for c0, layer in parts:
-            y = F.conv2d(xn, layer._w_src, layer.bias, stride=layer.stride, padding=layer.pad)
-            if residual is not None:
-                y = y + residual.permute(0, 3, 1, 2)[:, c0:c0 + layer.cout]
-            if layer.act == C.ACT_LEAKY:
-                y = torch.maximum(y, layer.act_a * y)
-            outs.append(y)
-        y = torch.cat(outs, 1)
-        assert y.shape[1] == cout
-        return y.permute(0, 2, 3, 1).contiguous()
-
-    def to_nhwc(x, out=None, out_coff=0, **_):
-        out[..., out_coff:out_coff + x.shape[1]].copy_(x.permute(0, 2, 3, 1))
-        return out
-    monkeypatch.setattr(M.ResnetEncoder, "_run_parts", staticmethod(run_parts))
-    monkeypatch.setattr(C, "maxpool3s2", lambda x: F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous())
-    monkeypatch.setattr(C, "nchw_to_nhwc", to_nhwc)
-    monkeypatch.setattr(C, "act_dtype", lambda: torch.float32)
-    x = torch.rand(2, 3, 64, 96)
-    with torch.no_grad():
-        ref = [t.clone() for t in enc._forward_folded(x)]
-        got = enc._forward_engine(x)
-    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in ref]
-    for a, b in zip(ref, got):
-        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max())
+    assert s1.wtc(True)[2] == (32 if C.K32 else 64) and s2.wtc(True)[2] == (32 if C.K32 else 64)
