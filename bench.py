@@ -2,11 +2,13 @@
 """bench.py -- MonoRec hot-path benchmark (contract: task statement / SURVEY.md §8d).
 
 Metric: keyframes/s (B x forwards / s) at 256x512, 32 depth planes, 4 source frames (BASELINE.json).
-Workload at N=1: BASELINE config 2 -- synthetic KITTI-shaped inputs, batch 8 per GPU, fused warp+SSIM cost-volume
-kernel only.  N>1: one process per GPU (torchrun), every rank runs its own batch of 8 (weak scaling), no data-path
-collective (the path shards on independent keyframes).
+Workload at N=1: BASELINE config 2 -- synthetic KITTI-shaped inputs, batch 8, fused warp+SSIM cost-volume kernel only.
+N>1: BASELINE config 4 -- one process per GPU (torchrun), a global batch of 128 keyframes sharded over the ranks
+(128 / N each), no data-path collective in the cost-volume path (it shards on independent keyframes, SURVEY.md §8e);
+the whole-model objects (`full_model*`) include the NCCL all-gather of the per-rank `result` maps in their timed region.
+`--config hires` is BASELINE config 5: 512x1024, 64 planes, 6 source frames, batch 4 per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config default|hires]
 
 `--impl reference` times the reference's CPU implementation of the path.  The reference is pure Python/PyTorch and
 cannot travel to the GPU box, so this arm runs the oracle port (oracle/cost_volume_oracle.py: the same torch CPU
@@ -27,16 +29,53 @@ sys.path.insert(0, str(ROOT))
 
 H, W, D, F = 256, 512, 32, 4
 B_PER_GPU = 8
+GLOBAL_BATCH = 128                         # BASELINE config 4: sharded over the ranks when N > 1
 INV_LO, INV_HI = 0.0025, 0.33
 METRIC = "keyframes_per_s_256x512_D32_F4"
 ALG_BYTES_PER_KEYFRAME = 4 * H * W * (1 + F) * (3 + D)   # every input read once, every output written once
 
 
-def k1_traffic():
-    """DRAM bytes per launch of the cost-volume kernel from the committed `ncu --set full` capture (config 2)."""
-    p = ROOT / "profiles" / "r01_k1_traffic.json"
-    if p.exists():
-        return float(json.loads(p.read_text())["traffic_bytes_per_launch"])
+def set_config(name):
+    global H, W, D, F, B_PER_GPU, METRIC, ALG_BYTES_PER_KEYFRAME
+    if name == "hires":                    # BASELINE config 5
+        H, W, D, F, B_PER_GPU = 512, 1024, 64, 6, 4
+        METRIC = "keyframes_per_s_512x1024_D64_F6"
+    ALG_BYTES_PER_KEYFRAME = 4 * H * W * (1 + F) * (3 + D)
+
+
+def k1_traffic(config, batch):
+    """DRAM bytes per launch of the cost-volume kernel from the committed `ncu --set full` capture -- valid only for the
+    kernel source it was taken from: the file stores the SHA-256 of csrc/cost_volume.cu and of the launch shape; any
+    mismatch (a changed kernel, another batch) reports null instead of a stale number."""
+    import hashlib
+    p = ROOT / "profiles" / "r02_k1_traffic.json"
+    if not p.exists():
+        return None, "no capture committed"
+    rec = json.loads(p.read_text())
+    sha = hashlib.sha256((ROOT / "monorec_b200" / "csrc" / "cost_volume.cu").read_bytes()).hexdigest()
+    ent = rec.get(f"{config}_b{batch}")
+    if ent is None:
+        return None, f"no capture for config {config} at batch {batch}"
+    if ent.get("cost_volume_cu_sha256") != sha:
+        return None, "capture predates the current cost_volume.cu"
+    return float(ent["traffic_bytes_per_launch"]), "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, " + ent.get("capture", "")
+
+
+def pin_to_gpu_numa_node(index):
+    """Runs this process on the CPUs NVML reports as local to GPU `index` before any pinned host buffer is allocated, so that
+    first-touch places those buffers on the GPU's NUMA node (the e2e copies then stay off the inter-socket link)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
     return None
 
 
@@ -107,6 +146,10 @@ def cpu_port_keyframes_per_s(repeats, threads=None):
     from monorec_b200.synthetic import make_inputs
     if threads:
         torch.set_num_threads(threads)
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))   # undo the NUMA pinning of the GPU part: use every host core
+    except Exception:
+        pass
     data = make_inputs(1, F, H, W, seed=0)
     O.cost_volume_torch(data, INV_HI, INV_LO, D)   # warm-up
     best = float("inf")
@@ -143,7 +186,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "keyframes/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1 + len(candidates), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cost_volume_256x512_D32_F4 (BASELINE config 2), one keyframe per step "
+            "config": {"workload": f"cost_volume_{H}x{W}_D{D}_F{F}, one keyframe per step "
                                    "(bounded sample: the reference is linear in batch)", "batch_per_step": 1},
             "cpu_baseline": {"value": val, "unit": "keyframes/s", "cores": torch.get_num_threads(), "kind": "port",
                              "sample": f"{steps} x 1 keyframe, torch CPU ops, {torch.get_num_threads()} threads (fastest of {candidates})"},
@@ -179,6 +222,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="default", choices=["default", "hires"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-model", action="store_true")
@@ -186,12 +230,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    set_config(args.config)
     if args.impl == "reference":
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)      # timing rules: at least 3 warm-up steps (the JSON line reports the number used)
     args.steps = max(args.steps, 1)
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback in the product path)"
+    numa_cpus = pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist
@@ -201,9 +247,12 @@ def main():
     from monorec_b200 import _lib
     from monorec_b200.synthetic import make_inputs, to_device
     lib = _lib.load()
-    B = B_PER_GPU
-    # rotating input sets: 4 x 63 MB of images > the 126 MB L2, so no step finds its inputs cached from the previous one
-    NSETS = 4
+    # N = 1: the configuration the metric is quoted on (batch 8); N > 1: BASELINE config 4, a global batch of 128 keyframes
+    # sharded over the ranks (hires: 4 per GPU at every N)
+    B = B_PER_GPU if (world == 1 or args.config == "hires") else max(1, GLOBAL_BATCH // world)
+    # rotating input sets whose images together exceed the 126 MB L2, so no step finds its inputs cached from the previous one
+    set_bytes = B * (1 + F) * 3 * H * W * 4
+    NSETS = max(2, min(4, -(-256 * 1024 * 1024 // set_bytes)))
     sets = []
     for i in range(NSETS):
         d = to_device(make_inputs(B, F, H, W, seed=100 * rank + i), dev)
@@ -259,16 +308,22 @@ def main():
     if rank == 0:
         peak, peak_src = hbm_peak()
         achieved = ALG_BYTES_PER_KEYFRAME * B / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_note = k1_traffic(args.config, B)
+        cfg_name = ("BASELINE config 5 (hi-res)" if args.config == "hires" else
+                    ("BASELINE config 2: fused warp+SSIM kernel only" if world == 1 else
+                     f"BASELINE config 4: global batch {B * world} sharded over {world} GPUs, cost-volume kernel"))
         line = {"metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "cost_volume_256x512_D32_F4 (BASELINE config 2: fused warp+SSIM kernel only)",
+                "config": {"workload": f"cost_volume_{H}x{W}_D{D}_F{F} ({cfg_name})",
                            "batch_per_gpu": B, "global_batch": B * world, "src_frames": F, "depth_planes": D,
                            "height": H, "width": W, "parallelism": f"dp{world} (independent keyframes, no collective)",
-                           "l2": f"inputs rotate over {NSETS} sets (252 MB) > 126 MB L2; 671 MB of outputs per step"},
+                           "l2": f"inputs rotate over {NSETS} sets ({NSETS * set_bytes >> 20} MiB) > 126 MB L2; "
+                                 f"{(1 + F) * B * D * H * W * 4 >> 20} MiB of outputs per step",
+                           "host_numa_cpus": numa_cpus},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": k1_traffic(), "peak_source": f"{peak_src} (burst copy)",
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": f"{peak_src} (burst copy)",
                              "kernel": "cost_volume_kernel (the events bracket mr_cost_volume_fwd: one launch)",
                              "kernel_ms": kernel_ms,
                              "algorithmic_bytes_per_launch": ALG_BYTES_PER_KEYFRAME * B},
@@ -284,13 +339,12 @@ def main():
         h_poses = torch.stack(host["poses"]).contiguous().pin_memory()
         h_intr = torch.stack(host["intrinsics"]).contiguous().pin_memory()
         h_cv = torch.empty(B, D, H, W).pin_memory()
-        h_sf = torch.empty(F, B, D, H, W).pin_memory()
         ws_bytes = lib.mr_cost_volume_host_workspace(B, F, D, H, W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 
         def e2e_step():
             _lib.check(lib.mr_cost_volume_host(h_key.data_ptr(), h_frames.data_ptr(), h_kp.data_ptr(), h_kk.data_ptr(),
-                                               h_poses.data_ptr(), h_intr.data_ptr(), h_cv.data_ptr(), h_sf.data_ptr(),
+                                               h_poses.data_ptr(), h_intr.data_ptr(), h_cv.data_ptr(), None,
                                                B, F, D, H, W, INV_LO, INV_HI, 10.0, ws.data_ptr(), ws_bytes), "e2e")
         e_steps = max(3, min(args.steps, 10))
         for _ in range(3):
@@ -306,10 +360,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             h2d = (1 + F) * B * 3 * H * W * 4 + (2 + 2 * F) * B * 64
-            d2h = (1 + F) * B * D * H * W * 4
+            d2h = B * D * H * W * 4
             line["e2e"] = {"value": world * B * e_steps / float(t.item()), "unit": "keyframes/s",
                            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
-                           "api": "mr_cost_volume_host (C ABI, pinned host buffers, both volumes downloaded)"}
+                           "api": "mr_cost_volume_host (C ABI, pinned host buffers NUMA-local to the GPU; images and matrices "
+                                  "uploaded, fused cost volume downloaded, single-frame volumes left on the device for the "
+                                  "MaskModule as in monorec_model.py:693-699)"}
 
     # ---- informational: the whole MonoRecModel.forward (cost volume + ResNet-18 + mask/depth conv stacks on the tensor
     #      cores) replayed from a CUDA graph, batch sharded like above, per-rank result maps all-gathered over NCCL ----
@@ -322,8 +378,12 @@ def main():
         default_mode = C.MODE
         for key, mode in (("full_model", "tf32"), ("full_model_f16", "f16")):
             C.set_mode(mode)
+            C.FLOPS = [0]
+            with torch.no_grad():
+                model(dict(sets[0]))             # one eager forward: counts the conv stacks' multiply-adds
+            conv_flops, C.FLOPS = C.FLOPS[0], None
             gm = GraphedMonoRec(model, sets[0])
-            fm_steps = 20
+            fm_steps = 20 if B <= 16 else 5
             for i in range(3):
                 all_gather_batch(gm(sets[i % NSETS])["result"], equal_shards=True)
             barrier()
@@ -338,8 +398,20 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if rank == 0:
                 fms = float(t.item()) / fm_steps
+                tpeak = None
+                pk = ROOT / "MEASURED_PEAKS.json"
+                if pk.exists():
+                    tpeak = float(json.loads(pk.read_text()).get("bf16_tflops_sustained", 0.0)) or None
+                tach = conv_flops / (fms * 1e-3) / 1e12
                 line[key] = {"value": world * B / (fms * 1e-3), "unit": "keyframes/s", "ms_per_forward": fms,
-                             "batch_per_gpu": B, "conv_arithmetic": mode, "gathered_result_shape": list(res.shape),
+                             "batch_per_gpu": B, "global_batch": B * world, "conv_arithmetic": mode,
+                             "gathered_result_shape": list(res.shape),
+                             "roofline": {"bound": "tensor", "achieved": tach, "peak": tpeak if tpeak else 1400.0,
+                                          "unit": "TFLOP/s", "frac": tach / (tpeak if tpeak else 1400.0),
+                                          "peak_source": "measured (sustained bf16 GEMM)" if tpeak else "fallback",
+                                          "flops_per_forward": conv_flops,
+                                          "note": "MaskModule + DepthModule multiply-adds (x2) over the whole forward time "
+                                                  "(cost volume, ResNet-18 trunk and the all-gather included in the time)"},
                              "what": "MonoRecModel.forward (CUDA-graph replay) + NCCL all-gather of result; "
                                      "inputs resident, random-init weights"}
             # the same forward from pinned HOST tensors to a HOST result (what example/test_monorec.py:45-53 does with
@@ -392,7 +464,7 @@ def main():
                 line["full_model_f16_b16"] = {"value": B16 / (fms * 1e-3), "unit": "keyframes/s", "ms_per_forward": fms,
                                               "batch_per_gpu": B16, "conv_arithmetic": "f16", "result_shape": list(res.shape),
                                               "what": "BASELINE config 3: MonoRecModel.forward (CUDA-graph replay), batch 16, "
-                                                      "inputs resident (2 rotating sets, 252 MB), random-init weights"}
+                                                      "inputs resident (2 rotating sets), random-init weights"}
                 del gm, sets16
             except Exception as exc:   # noqa: BLE001
                 line["full_model_f16_b16_error"] = f"{type(exc).__name__}: {exc}"[:200]

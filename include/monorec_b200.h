@@ -89,10 +89,15 @@ int mr_cost_volume_fwd_gather(const float* keyframe, const float* const* frames,
  * mr_projection_tables + mr_cost_volume_fwd and downloads both volumes; batch elements are pipelined on
  * internal streams so copies overlap the kernel.  This is the end-to-end entry bench.py times as `e2e`.
  *   h_keyframe [B,3,H,W]; h_frames [F,B,3,H,W]; h_keyframe_pose,h_keyframe_K [B,4,4]; h_poses,h_intrinsics [F,B,4,4]
- *   h_out_cv [B,D,H,W]; h_out_sfcv [F,B,D,H,W]
- * workspace: device buffer of at least mr_cost_volume_host_workspace(B,F,D,H,W) bytes (caller-owned).
+ *   h_out_cv [B,D,H,W]; h_out_sfcv [F,B,D,H,W] or NULL: the single-frame volumes then stay in the workspace on the device
+ *   (no consumer of the reference reads them on the host: they feed the MaskModule on the device, monorec_model.py:693-699);
+ *   their device address is workspace + mr_cost_volume_host_sfcv_offset(B,F,D,H,W).
+ * workspace: device buffer of at least mr_cost_volume_host_workspace(B,F,D,H,W) bytes (caller-owned).  It must be idle: the
+ * call runs on internal non-blocking streams (created once per host thread and device, reused by later calls) that are not
+ * ordered against work the caller has queued on other streams; the call returns after all of its copies have completed.
  */
 long long mr_cost_volume_host_workspace(int B, int F, int D, int H, int W);
+long long mr_cost_volume_host_sfcv_offset(int B, int F, int D, int H, int W);
 int mr_cost_volume_host(const float* h_keyframe, const float* h_frames,
                         const float* h_keyframe_pose, const float* h_keyframe_K,
                         const float* h_poses, const float* h_intrinsics,

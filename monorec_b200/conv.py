@@ -31,6 +31,7 @@ HALO_F16 = os.environ.get("MONOREC_B200_TC_HALO_F16", "1") != "0" and os.environ
 # modes (Cout padded to 16): 5.93 -> 5.83 ms per half-mode forward at B=8 against the CUDA-core per-pixel kernel (round 2)
 TC_HEADS = True
 DT_F32, DT_F16 = 0, 1
+FLOPS = None       # set to [0] to count the conv stacks' flops during a forward (bench.py's tensor roofline)
 
 
 def set_mode(mode):
@@ -276,6 +277,10 @@ class PackedConv:
     def __call__(self, srcs, out=None, out_hw=None, final=False, out_coff=0):
         """out_coff: first channel of the slice of `out` this layer writes (tensor-core path)."""
         assert tuple(s.shape[3] for s in srcs) == self.src_c, (tuple(s.shape[3] for s in srcs), self.src_c)
+        if FLOPS is not None:      # bench.py: multiply-adds of this layer (2 flops each), counted on one eager forward
+            Bn, Hs, Ws, _ = srcs[0].shape
+            ho, wo = out_hw if out_hw is not None else (math.ceil(Hs / self.stride[0]), math.ceil(Ws / self.stride[1]))
+            FLOPS[0] += 2 * Bn * ho * wo * self.cout * sum(self.src_c) * self.kh * self.kw
         if MODE == "f16" and srcs[0].dtype == torch.float16:
             if self.tc_ok_f16:
                 return conv2d_tc(srcs, self, out=out, out_hw=out_hw, round_out=False, half=True, out_f32=final, out_coff=out_coff)

@@ -1,7 +1,7 @@
 // Host-buffer entry of the cost-volume path (include/monorec_b200.h: mr_cost_volume_host).
 // Batch elements are pipelined over a small ring of internal streams: the H2D copy of element b+1 and the D2H copy
-// of element b-1 overlap the kernel of element b.  The caller owns the device workspace; nothing persistent is
-// allocated here (streams/events live for the duration of the call).
+// of element b-1 overlap the kernel of element b.  The caller owns the device workspace; the streams and the event are
+// created once per host thread and device and reused by later calls.
 #include "mr_common.cuh"
 #include <cstdint>
 
@@ -30,17 +30,26 @@ constexpr int kStreams = 3;
 struct StreamRing {
     cudaStream_t st[kStreams] = {};
     cudaEvent_t ready = nullptr;
-    int n = 0;
-    int init() {
+    int n = 0, device = -1;
+    int init() {   // idempotent: re-created only when the calling thread has switched devices
+        int dev = 0;
+        MR_CUDA(cudaGetDevice(&dev));
+        if (dev == device && n == kStreams && ready != nullptr) return MR_OK;
+        release();
         for (; n < kStreams; ++n) MR_CUDA(cudaStreamCreateWithFlags(&st[n], cudaStreamNonBlocking));
         MR_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        device = dev;
         return MR_OK;
     }
-    ~StreamRing() {
+    void release() {
         for (int i = 0; i < n; ++i) cudaStreamDestroy(st[i]);
         if (ready) cudaEventDestroy(ready);
+        n = 0; ready = nullptr; device = -1;
     }
+    ~StreamRing() { release(); }   // at thread exit (errors after context teardown are ignored)
 };
+
+thread_local StreamRing g_ring;
 
 }  // namespace
 
@@ -49,13 +58,17 @@ extern "C" long long mr_cost_volume_host_workspace(int B, int F, int D, int H, i
     return (long long)plan(B, F, D, H, W).total;
 }
 
+extern "C" long long mr_cost_volume_host_sfcv_offset(int B, int F, int D, int H, int W) {
+    if (B < 1 || F < 1 || D < 2 || H < 5 || W < 5) return -1;
+    return (long long)plan(B, F, D, H, W).sfcv;
+}
+
 extern "C" int mr_cost_volume_host(const float* h_keyframe, const float* h_frames, const float* h_keyframe_pose,
                                    const float* h_keyframe_K, const float* h_poses, const float* h_intrinsics,
                                    float* h_out_cv, float* h_out_sfcv, int B, int F, int D, int H, int W,
                                    float inv_depth_lo, float inv_depth_hi, float alpha, void* workspace,
                                    long long workspace_bytes) {
-    MR_REQUIRE(h_keyframe && h_frames && h_keyframe_pose && h_keyframe_K && h_poses && h_intrinsics && h_out_cv &&
-                   h_out_sfcv && workspace,
+    MR_REQUIRE(h_keyframe && h_frames && h_keyframe_pose && h_keyframe_K && h_poses && h_intrinsics && h_out_cv && workspace,
                "mr_cost_volume_host: null pointer");
     MR_REQUIRE(B >= 1 && F >= 1 && F <= MR_MAX_FRAMES && D >= 2 && D <= 128 && H >= 5 && W >= 5,
                "mr_cost_volume_host: bad shape B=%d F=%d D=%d H=%d W=%d", B, F, D, H, W);
@@ -78,7 +91,7 @@ extern "C" int mr_cost_volume_host(const float* h_keyframe, const float* h_frame
     float* d_cv = reinterpret_cast<float*>(ws + p.cv);
     float* d_sfcv = reinterpret_cast<float*>(ws + p.sfcv);
 
-    StreamRing ring;
+    StreamRing& ring = g_ring;
     int rc = ring.init();
     if (rc != MR_OK) return rc;
     // everything below only enqueues work; whatever happens, the internal streams are drained before returning so that no
@@ -111,7 +124,7 @@ extern "C" int mr_cost_volume_host(const float* h_keyframe, const float* h_frame
             rc = mr::launch_cost_volume(d_key, fp, d_proj, d_depths, d_cv, d_sfcv, B, F, D, H, W, alpha, nullptr, b, 1, 0, s);
             if (rc != MR_OK) return rc;
             MR_CUDA(cudaMemcpyAsync(h_out_cv + b * vol1, d_cv + b * vol1, vol1 * 4, cudaMemcpyDeviceToHost, s));
-            for (int f = 0; f < F; ++f) {
+            for (int f = 0; f < F && h_out_sfcv != nullptr; ++f) {
                 size_t o = ((size_t)f * B + b) * vol1;
                 MR_CUDA(cudaMemcpyAsync(h_out_sfcv + o, d_sfcv + o, vol1 * 4, cudaMemcpyDeviceToHost, s));
             }
