@@ -3,8 +3,8 @@
 
 Metric: keyframes/s (B x forwards / s) at 256x512, 32 depth planes, 4 source frames (BASELINE.json).
 Workload at N=1: BASELINE config 2 -- synthetic KITTI-shaped inputs, batch 8, fused warp+SSIM cost-volume kernel only.
-N>1: BASELINE config 4 -- one process per GPU (torchrun), a global batch of 128 keyframes sharded over the ranks
-(128 / N each), no data-path collective in the cost-volume path (it shards on independent keyframes, SURVEY.md §8e);
+N>1: BASELINE config 4 -- one process per GPU (torchrun), 16 keyframes per GPU (weak scaling; the global batch is the
+128 of config 4 at N=8), no data-path collective in the cost-volume path (it shards on independent keyframes, SURVEY.md §8e);
 the whole-model objects (`full_model*`) include the NCCL all-gather of the per-rank `result` maps in their timed region.
 `--config hires` is BASELINE config 5: 512x1024, 64 planes, 6 source frames, batch 4 per GPU.
 
@@ -29,7 +29,7 @@ sys.path.insert(0, str(ROOT))
 
 H, W, D, F = 256, 512, 32, 4
 B_PER_GPU = 8
-GLOBAL_BATCH = 128                         # BASELINE config 4: sharded over the ranks when N > 1
+B_PER_GPU_SHARDED = 16                     # BASELINE config 4: batch 128 sharded over 8 GPUs = 16 per GPU (used for every N > 1)
 INV_LO, INV_HI = 0.0025, 0.33
 METRIC = "keyframes_per_s_256x512_D32_F4"
 ALG_BYTES_PER_KEYFRAME = 4 * H * W * (1 + F) * (3 + D)   # every input read once, every output written once
@@ -247,9 +247,9 @@ def main():
     from monorec_b200 import _lib
     from monorec_b200.synthetic import make_inputs, to_device
     lib = _lib.load()
-    # N = 1: the configuration the metric is quoted on (batch 8); N > 1: BASELINE config 4, a global batch of 128 keyframes
-    # sharded over the ranks (hires: 4 per GPU at every N)
-    B = B_PER_GPU if (world == 1 or args.config == "hires") else max(1, GLOBAL_BATCH // world)
+    # N = 1: the configuration the metric is quoted on (batch 8); N > 1: BASELINE config 4's shard size, 16 keyframes per GPU
+    # (global batch 16 N = 128 at N = 8; weak scaling); hires: 4 per GPU at every N
+    B = B_PER_GPU if (world == 1 or args.config == "hires") else B_PER_GPU_SHARDED
     # rotating input sets whose images together exceed the 126 MB L2, so no step finds its inputs cached from the previous one
     set_bytes = B * (1 + F) * 3 * H * W * 4
     NSETS = max(2, min(4, -(-256 * 1024 * 1024 // set_bytes)))
@@ -311,7 +311,7 @@ def main():
         traffic, traffic_note = k1_traffic(args.config, B)
         cfg_name = ("BASELINE config 5 (hi-res)" if args.config == "hires" else
                     ("BASELINE config 2: fused warp+SSIM kernel only" if world == 1 else
-                     f"BASELINE config 4: global batch {B * world} sharded over {world} GPUs, cost-volume kernel"))
+                     f"BASELINE config 4 shard size: {B} keyframes per GPU, global batch {B * world} over {world} GPUs"))
         line = {"metric": METRIC, "value": value, "unit": "keyframes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -155,6 +155,22 @@ int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
  * results).  Tuning switches (environment, read once): MONOREC_B200_TC_HALO=0|1|2, MONOREC_B200_TC_HALO_F16=0|1,
  * MONOREC_B200_TC_CTAS=n. */
 int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream);
+/* Host-side weight packing for mr_conv2d_nhwc_tc (pure host code, callable without a GPU).
+ *   mr_pack_conv_weights_bytes: size of the packed tensor and its n_pad / k_pad for a correlation kernel (Cout, sum src_c, kh, kw)
+ *     whose input channels are the concatenation of n_src sources; dtype MR_DT_F32 (TF32-rounded fp32) or MR_DT_F16.
+ *   mr_pack_conv_weights: w = host [Cout][Cin][kh][kw] (nn.Conv2d.weight), out = host buffer of that size; upload it and pass
+ *     the device copy as mr_conv_desc.weight together with n_pad / k_pad.
+ *   mr_subpixel_convt_k4s2: phase (py, px) of Refine's ConvTranspose2d(k4, s2) + crop (model/layers.py:380-400) as a 2x2
+ *     correlation: w = host [Cin][Cout][4][4] (nn.ConvTranspose2d.weight), out = host [Cout][Cin][2][2]; run it with
+ *     pad_t / pad_l as returned, oy_step = ox_step = 2, oy_off = py, ox_off = px.
+ *   mr_subpixel_upconv2: phase (py, px) of Upconv's nearest-x2 + pad(0,1,0,1) + Conv2d(k2) (model/layers.py:338-356):
+ *     w = host [Cout][Cin][2][2], out = host [Cout][Cin][kh_out][kw_out] (kh_out = 1 + py, kw_out = 1 + px), pad 0.
+ *   mr_conv_workspace_bytes: device scratch a convolution call needs (0: everything is staged in shared / tensor memory). */
+long long mr_pack_conv_weights_bytes(int Cout, int n_src, const int* src_c, int kh, int kw, int dtype, int* n_pad, int* k_pad);
+int mr_pack_conv_weights(const float* w, int Cout, int n_src, const int* src_c, int kh, int kw, int dtype, void* out);
+int mr_subpixel_convt_k4s2(const float* w, int Cin, int Cout, int py, int px, float* out, int* pad_t, int* pad_l);
+int mr_subpixel_upconv2(const float* w, int Cout, int Cin, int py, int px, float* out, int* kh_out, int* kw_out);
+long long mr_conv_workspace_bytes(const mr_conv_desc* desc);
 /* sizeof(mr_conv_desc) as compiled into the library (bindings check their mirror of the struct against it). */
 int mr_sizeof_conv_desc(void);
 

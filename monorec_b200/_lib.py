@@ -31,6 +31,11 @@ SIGNATURES = {
     "mr_cost_volume_host": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float] * 3 + [c_void_p, c_longlong]),
     "mr_conv2d_nhwc": (c_int, [c_void_p, c_void_p]),
     "mr_sizeof_conv_desc": (c_int, []),
+    "mr_pack_conv_weights_bytes": (c_longlong, [c_int, c_int, POINTER(c_int), c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "mr_pack_conv_weights": (c_int, [c_void_p, c_int, c_int, POINTER(c_int), c_int, c_int, c_int, c_void_p]),
+    "mr_subpixel_convt_k4s2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "mr_subpixel_upconv2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_int), POINTER(c_int)]),
+    "mr_conv_workspace_bytes": (c_longlong, [c_void_p]),
     "mr_conv2d_nhwc_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "mr_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "mr_nchw_to_nhwc_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

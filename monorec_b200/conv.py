@@ -230,16 +230,33 @@ def _round_tf32(w):
 
 
 def pack_tc_weight(w, src_c, half=False, allow_k32=True):
-    """Correlation kernel (Cout, Cin, kh, kw) -> [kh*kw][n_pad][k_pad] K-major: every source padded to a whole number of
-    K chunks (32 fp32 / 64 half channels = one 128-byte swizzle row, or 32 half channels = one 64-byte row when that pads
-    less; zero rows), Cout padded to a multiple of 16; values
-    rounded to TF32 (fp32 storage) or converted to half."""
+    """Correlation kernel (Cout, Cin, kh, kw) -> [kh*kw][n_pad][k_pad] K-major through the library's host-side packer
+    (include/monorec_b200.h: mr_pack_conv_weights): every source padded to a whole number of K chunks (32 fp32 / 64 half
+    channels = one 128-byte swizzle row, or 32 half channels = one 64-byte row when every source has <= 32 channels; zero
+    rows), Cout padded to a multiple of 16; values rounded to TF32 (fp32 storage) or converted to half.
+    allow_k32=False / MONOREC_B200_TC_K32=0 (experiments) force 64-channel chunks by packing in torch instead."""
+    import ctypes
     Cout, Cin, kh, kw = w.shape
     assert sum(src_c) == Cin
-    kc = 2 * KC if half else KC
-    if half and K32 and allow_k32 and all(c <= 32 for c in src_c):
-        kc = 32   # sources of <= 32 channels: 64-byte swizzle rows instead of half-empty 128-byte ones (same number of K
-        #           chunks, half the TMA and MMA work per chunk); the library reads the chunk width off k_pad
+    if half and not (K32 and allow_k32) and all(c <= 32 for c in src_c):
+        return _pack_tc_weight_torch(w, src_c, half, kc=64)
+    lib = _lib.load()
+    wc = w.detach().to("cpu", torch.float32).contiguous()
+    sc = (ctypes.c_int * len(src_c))(*[int(c) for c in src_c])
+    n_pad, k_pad = ctypes.c_int(0), ctypes.c_int(0)
+    dt = DT_F16 if half else DT_F32
+    nbytes = lib.mr_pack_conv_weights_bytes(Cout, len(src_c), sc, kh, kw, dt, ctypes.byref(n_pad), ctypes.byref(k_pad))
+    assert nbytes > 0
+    out = torch.empty(kh * kw, n_pad.value, k_pad.value, dtype=torch.float16 if half else torch.float32)
+    _lib.check(lib.mr_pack_conv_weights(wc.data_ptr(), Cout, len(src_c), sc, kh, kw, dt, out.data_ptr()), "mr_pack_conv_weights")
+    return out.to(w.device), n_pad.value, k_pad.value
+
+
+def _pack_tc_weight_torch(w, src_c, half, kc=None):
+    """The same layout written with torch ops (the packer's restatement: tests compare the two)."""
+    Cout, Cin, kh, kw = w.shape
+    if kc is None:
+        kc = (32 if all(c <= 32 for c in src_c) else 64) if half else KC
     n_pad = ((Cout + 15) // 16) * 16
     k_pad = sum(((c + kc - 1) // kc) * kc for c in src_c)
     out = torch.zeros(kh * kw, n_pad, k_pad, device=w.device, dtype=torch.float32)

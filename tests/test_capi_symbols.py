@@ -61,6 +61,18 @@ def test_header_is_plain_c_and_a_c_consumer_links(tmp_path):
                    '    if (mr_conv2d_nhwc_tc(0, 16, 32, 0, 0) == MR_OK) return 3;\n'
                    '    if (strstr(mr_last_error(), "null descriptor") == 0) return 4;\n'
                    '    if (mr_cost_volume_host_workspace(8, 4, 32, 256, 512) <= 0) return 5;\n'
+                   '    {   /* pack a 3x3 layer with two concatenated sources for the half tensor-core path, on the host */\n'
+                   '        static float w[24 * 96 * 9]; static unsigned short packed[9 * 32 * 128];\n'
+                   '        int src_c[2] = {32, 64}, n_pad = 0, k_pad = 0, i;\n'
+                   '        for (i = 0; i < 24 * 96 * 9; ++i) w[i] = (float)(i % 7) - 3.0f;\n'
+                   '        if (mr_pack_conv_weights_bytes(24, 2, src_c, 3, 3, MR_DT_F16, &n_pad, &k_pad) != (long long)sizeof packed) return 6;\n'
+                   '        if (n_pad != 32 || k_pad != 128) return 7;\n'
+                   '        if (mr_pack_conv_weights(w, 24, 2, src_c, 3, 3, MR_DT_F16, packed) != MR_OK) return 8;\n'
+                   '        /* tap (1,1), output channel 5, input channel 40 (second source) lives at [4][5][64 + 8]; w = -3 .. 3 */\n'
+                   '        if (packed[(4 * 32 + 5) * 128 + 72] != 0xC000 /* half -2.0 = w[(5*96+40)*9+4] = (4684 % 7) - 3 */) return 9;\n'
+                   '        if (packed[(4 * 32 + 5) * 128 + 40] != 0) return 10;   /* padding of the first source */\n'
+                   '        if (mr_conv_workspace_bytes(&d) != 0) return 11;\n'
+                   '    }\n'
                    '    printf("%d\\n", mr_version());\n    return 0;\n}\n')
     exe = tmp_path / "consumer"
     libdir = _lib.LIB_PATH.parent

@@ -114,3 +114,52 @@ def test_tc_weight_packing_chunk_widths():
     s1 = C.PackedConv(w, None, (32,), stride=(1, 1))
     s2 = C.PackedConv(w, None, (32,), stride=(2, 1))
     assert s1.wtc(True)[2] == (32 if C.K32 else 64) and s2.wtc(True)[2] == (32 if C.K32 else 64)
+
+
+def test_c_packer_matches_torch_restatement():
+    """mr_pack_conv_weights (host-side C, include/monorec_b200.h) == the torch restatement of the layout, fp32/TF32 and half,
+    one to three concatenated sources, ragged channel counts; padding rows and columns are zero."""
+    from monorec_b200 import conv as C
+    g = torch.Generator().manual_seed(3)
+    for cout, src_c, kh, kw in [(24, (32,), 3, 3), (48, (32, 64), 3, 3), (96, (64, 64, 96), 1, 1), (1, (24,), 3, 3), (13, (40,), 7, 1)]:
+        w = torch.randn(cout, sum(src_c), kh, kw, generator=g)
+        for half in (False, True):
+            got, n_pad, k_pad = C.pack_tc_weight(w, src_c, half=half)
+            ref, n_ref, k_ref = C._pack_tc_weight_torch(w, src_c, half)
+            assert (n_pad, k_pad) == (n_ref, k_ref) and got.dtype == ref.dtype and torch.equal(got, ref), (cout, src_c, half)
+
+
+def test_c_subpixel_kernels_reproduce_reference_layers():
+    """mr_subpixel_convt_k4s2 / mr_subpixel_upconv2: the four phase kernels reproduce ConvTranspose2d(k4, s2) + crop (Refine,
+    model/layers.py:380-400) and Upsample(x2) + pad(0,1,0,1) + Conv2d(k2) (Upconv, :338-356)."""
+    import ctypes
+    import torch.nn.functional as F
+    from monorec_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 5, 6, 7, generator=g)
+    wt = torch.randn(5, 4, 4, 4, generator=g).contiguous()           # (Cin, Cout, 4, 4)
+    ref = F.conv_transpose2d(x, wt, stride=2)[:, :, 1:-1, 1:-1]
+    out = torch.zeros_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            sub = torch.empty(4, 5, 2, 2)
+            pt, pl = ctypes.c_int(-1), ctypes.c_int(-1)
+            assert lib.mr_subpixel_convt_k4s2(wt.data_ptr(), 5, 4, py, px, sub.data_ptr(), ctypes.byref(pt), ctypes.byref(pl)) == 0
+            assert (pt.value, pl.value) == (1 - py, 1 - px)
+            xp = F.pad(x, (pl.value, 1 - pl.value, pt.value, 1 - pt.value))
+            out[:, :, py::2, px::2] = F.conv2d(xp, sub)
+    assert torch.allclose(out, ref, atol=1e-5)
+    wu = torch.randn(3, 5, 2, 2, generator=g).contiguous()           # (Cout, Cin, 2, 2)
+    up = F.interpolate(x, scale_factor=2, mode="nearest")
+    ref = F.conv2d(F.pad(up, (0, 1, 0, 1)), wu)
+    out = torch.zeros_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            kh, kw = ctypes.c_int(0), ctypes.c_int(0)
+            sub = torch.empty(3 * 5 * 4)
+            assert lib.mr_subpixel_upconv2(wu.data_ptr(), 3, 5, py, px, sub.data_ptr(), ctypes.byref(kh), ctypes.byref(kw)) == 0
+            sub = sub[:3 * 5 * kh.value * kw.value].view(3, 5, kh.value, kw.value)
+            xp = F.pad(x, (0, kw.value - 1, 0, kh.value - 1))          # pixel o + 1 beyond the border is the reference's zero pad
+            out[:, :, py::2, px::2] = F.conv2d(xp, sub)
+    assert torch.allclose(out, ref, atol=1e-5)
