@@ -169,11 +169,15 @@ def nchw_to_nhwc(x, out=None, out_coff=0, one_minus=None, dtype=None):
     B, C, H, W = x.shape
     if out is None:
         out = torch.empty(B, H, W, C, device=x.device, dtype=dtype)
-    om = one_minus.contiguous().data_ptr() if one_minus is not None else None
+    om_t = None
+    if one_minus is not None:    # the kernel reads fp32 [B,1,H,W]: any other dtype / shape would be read out of bounds
+        om_t = one_minus.to(device=x.device, dtype=torch.float32).contiguous()
+        assert om_t.numel() == B * H * W, f"one_minus must hold one value per pixel (B,1,H,W), got {tuple(one_minus.shape)}"
     fn, name = (lib.mr_nchw_to_nhwc_f16, "mr_nchw_to_nhwc_f16") if out.dtype == torch.float16 else (lib.mr_nchw_to_nhwc, "mr_nchw_to_nhwc")
     with torch.cuda.device(x.device):
-        _lib.check(fn(x.data_ptr(), out.data_ptr(), B, C, H, W, out.shape[3], out_coff, om, _stream(x)), name)
-    return out
+        _lib.check(fn(x.data_ptr(), out.data_ptr(), B, C, H, W, out.shape[3], out_coff,
+                      om_t.data_ptr() if om_t is not None else None, _stream(x)), name)
+    return out        # (om_t stays referenced until the launch has been queued; the caching allocator is stream-ordered)
 
 
 def as_nhwc(x, dtype):

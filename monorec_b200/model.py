@@ -9,6 +9,7 @@ reference too; SURVEY.md §8f "next" row 1) with its eval-mode BatchNorms folded
 measured the trunk on the conv engine at 1.03 ms against cuDNN's 0.71 ms in half mode, so that variant was removed.)
 """
 import os
+import warnings
 
 import torch
 from torch import nn
@@ -62,12 +63,18 @@ class Refine(nn.Module):
 
 
 class _Packed:
-    """Kernel-layout copies of a module's parameters, rebuilt when a parameter changes (load_state_dict, .to(), step)."""
+    """Kernel-layout copies of a module's parameters, rebuilt when a parameter changes (load_state_dict, .to(), an optimizer
+    step: anything that bumps the tensors' version counters or moves them).  In-place edits through `.data` (e.g.
+    `p.data.copy_(ema)`) are invisible to autograd's version counter: call `invalidate()` (or the owning module's
+    `invalidate_packed_weights()`) after such an edit."""
 
     def __init__(self):
         self.sig, self.data = None, {}
 
-    def get(self, module, builder):
+    def invalidate(self):
+        self.sig = None
+
+    def get(self, module, builder):   # noqa: D401
         params = list(module.parameters())
         sig = (C.MODE,) + tuple((p.data_ptr(), p._version, str(p.device)) for p in params)
         if sig != self.sig:
@@ -96,12 +103,16 @@ class ResnetEncoder(nn.Module):
         # cache: a MonoRec checkpoint carries `_feature_extractor.encoder.*` anyway, and this code must stay silent and
         # offline-safe (no download attempt, nothing printed to stdout).
         weights = None
+        self.pretrained_requested_but_missing = False
         if pretrained:
             import os
             w = torchvision.models.ResNet18_Weights.IMAGENET1K_V1
             cached = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
             if os.path.isfile(cached):
                 weights = w
+            else:
+                # the reference would download them here; MonoRecModel warns if no checkpoint supplies the encoder either
+                self.pretrained_requested_but_missing = True
         self.encoder = torchvision.models.resnet18(weights=weights)
 
     # ---- inference fast path: BatchNorm (eval mode = a fixed per-channel affine) folded into the preceding convolution ----
@@ -113,6 +124,10 @@ class ResnetEncoder(nn.Module):
         if conv.bias is not None:
             b = b + conv.bias * scale
         return w, b.contiguous()
+
+    def invalidate_packed_weights(self):
+        """Forget the folded / packed copies (needed only after in-place `.data` edits of the parameters or BatchNorm buffers)."""
+        self._fold_sig = None
 
     def _folded(self):
         e = self.encoder
@@ -190,6 +205,10 @@ class MaskModule(nn.Module):
             nn.Sequential(Upconv(d[2], d[2]), ConvReLU(d[2] + e[0], d[3], 3), ConvReLU(d[3], d[3], 3))])
         self.classifier = nn.Sequential(nn.Conv2d(d[3], 1, kernel_size=1, stride=1), nn.Sigmoid())
         self._packed = _Packed()
+
+    def invalidate_packed_weights(self):
+        """After in-place `.data` edits of the parameters (not seen by the version counters): repack on the next call."""
+        self._packed.invalidate()
 
     def _build(self):
         e, d, fc = self._cv_enc_feat_chns, self._dec_feat_chns, self.feat_chns
@@ -274,6 +293,10 @@ class DepthModule(nn.Module):
                                          for ch in d[:3] + d[-1:]])
         self._packed = _Packed()
         self.out_range = (0.0, 1.0)   # (a, b): heads emit a + b * |tanh|; MonoRecModel folds the inverse-depth affine in
+
+    def invalidate_packed_weights(self):
+        """After in-place `.data` edits of the parameters (not seen by the version counters): repack on the next call."""
+        self._packed.invalidate()
 
     def _build(self):
         e, d, fc = self._cv_enc_feat_chns, self._dec_feat_chns, self.feat_chns
@@ -398,6 +421,14 @@ class MonoRecModel(nn.Module):
         self.augmenter = None
         self._trunk_channels_last = False
 
+    def invalidate_packed_weights(self):
+        """Forget every kernel-layout copy of the parameters (folded trunk, packed conv stacks).  Only needed after edits
+        that bypass the tensors' version counters, e.g. `p.data.copy_(ema)`; load_state_dict / .to() / optimizer steps are
+        detected automatically."""
+        for m in self.modules():
+            if m is not self and hasattr(m, "invalidate_packed_weights"):
+                m.invalidate_packed_weights()
+
     # -- checkpoint loading: same key filtering as utils/util.py:244-248 + monorec_model.py:630-657 ------------------
     @staticmethod
     def filter_state_dict(state_dict, data_parallel=False):
@@ -413,9 +444,19 @@ class MonoRecModel(nn.Module):
         def read(cp):
             checkpoint = torch.load(cp, map_location=torch.device("cpu"), weights_only=False)
             return self.filter_state_dict(checkpoint["state_dict"], checkpoint["arch"] == "DataParallel")
+        encoder_loaded = False
         if checkpoint_location is not None:
             for cp in as_list(checkpoint_location):
-                self.load_state_dict(read(cp), strict=False)
+                sd = read(cp)
+                res = self.load_state_dict(sd, strict=False)
+                encoder_loaded = encoder_loaded or any(k.startswith("_feature_extractor.") for k in sd)
+                if res.missing_keys:
+                    warnings.warn(f"monorec_b200: {cp} leaves {len(res.missing_keys)} parameters at their initial values "
+                                  f"(first: {res.missing_keys[0]})")
+        if getattr(self._feature_extractor, "pretrained_requested_but_missing", False) and not encoder_loaded:
+            # the reference always has ImageNet weights at this point (torchvision downloads them, monorec_model.py:104-113)
+            warnings.warn("monorec_b200: ResnetEncoder(pretrained=True) found no ImageNet weights in the local hub cache and no "
+                          "checkpoint supplied `_feature_extractor.*`: the trunk is randomly initialised")
         if mask_cp_loc is not None:
             for cp in as_list(mask_cp_loc):
                 sd = read(cp)
@@ -450,7 +491,9 @@ class MonoRecModel(nn.Module):
             if not self._trunk_channels_last:
                 self._feature_extractor.to(memory_format=torch.channels_last)
                 self._trunk_channels_last = True
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=(C.MODE != "fp32")):
+            # (only TF32 is decided here: the caller's cuDNN benchmark / deterministic settings are passed through)
+            with torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                            deterministic=torch.backends.cudnn.deterministic, allow_tf32=(C.MODE != "fp32")):
                 data_dict["image_features"] = self._feature_extractor(
                     (keyframe + .5).contiguous(memory_format=torch.channels_last))
 
@@ -466,8 +509,12 @@ class MonoRecModel(nn.Module):
                 # cost_volume * (1 - cv_mask) (:713): the product is fused into the depth module's layout change and
                 # the masked volume is also materialised for callers that read data_dict["cost_volume"]
                 data_dict["_cv_mask_for_depth"] = data_dict["cv_mask"]
+                saved_range = self.depth_module.out_range
                 self.depth_module.out_range = (lo, hi - lo)               # (1-p)*lo + p*hi, :717-718
-                data_dict = self.depth_module(data_dict)
+                try:
+                    data_dict = self.depth_module(data_dict)
+                finally:       # a standalone DepthModule call keeps returning the reference's raw |tanh| heads
+                    self.depth_module.out_range = saved_range
                 del data_dict["_cv_mask_for_depth"]
                 data_dict["cost_volume"] = C.mask_volume(data_dict["cost_volume"], data_dict["cv_mask"])
 
