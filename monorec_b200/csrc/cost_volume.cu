@@ -56,9 +56,6 @@ constexpr int kRowStride = 68;  // floats per smem image row: column b lives at 
 #ifndef MR_CV_TILE_ROWS
 #define MR_CV_TILE_ROWS 16
 #endif
-#ifndef MR_CV_PP
-#define MR_CV_PP 1              // per-pixel phase: 1 = next frame's planes requested during the current frame's arithmetic
-#endif
 #ifndef MR_CV_SKIP
 #define MR_CV_SKIP 0            // timing experiments only: 1 = no march, 2 = no per-pixel phase, 3 = march without stage 2, 4 = without stage 1
 #endif
@@ -808,175 +805,119 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
     // ---- per-pixel phase: view weights (monorec_model.py:257-260), zeroing of invalid pixels (:251) and fusion
     //      cv = sum_f w_f (1 - 2 sad_f) / sum_f w_f, 0 where sum_f w_f == 0 (:262-269).  Each thread reads back the
     //      L2-hot single-frame values of its pixel once per frame. ------------------------------------------------------
-#if MR_CV_PP == 0
-    const float na4 = -0.25f * a.alpha;
-    for (int p = tid; p < TH * kTileCols && MR_CV_SKIP != 2; p += kThreads) {
-        const int r = p >> 6, bc = p & 63;
-        const int u = u0 + bc, v = v0 + r;
-        const bool own = (bc >= 2) && (bc < 2 + kOutCols) && (u < W) && (v < H);
-        if (!own) continue;
-        const size_t pix = (size_t)v * W + u;
-        float* cv_out = a.cv + (size_t)b * D * plane + pix;
-        for (int d0 = 0; d0 < D; d0 += kChunk) {   // one pass when D <= kChunk
-            float acc[kChunk];
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
-            float wsum = 0.f;
-            for (int f = 0; f < F; ++f) {
-                float* sf = a.sfcv + (((size_t)f * a.B + b) * D) * plane + pix;
-                if (vmask[f * TH * kTileCols + p] == 0) {
-                    if (d0 == 0)
-                        for (int d = 0; d < D; ++d) sf[(size_t)d * plane] = 0.f;
-                    continue;
-                }
-                // sad = (1 - sv) / 2, so (sad - min sad)^2 = ((max sv - sv) / 2)^2
-                float m = -2.0f, sum = 0.f;
-                float vv[kChunk];
-                if (D <= kChunk) {
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) vv[j] = (j < D) ? __ldcg(sf + (size_t)j * plane) : -2.0f;
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) m = fmaxf(m, vv[j]);
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) {
-                        const float df = m - vv[j];
-                        if (j < D) sum += __expf(na4 * df * df);
-                    }
-                } else {
-                    for (int d = 0; d < D; ++d) m = fmaxf(m, __ldcg(sf + (size_t)d * plane));
-                    for (int d = 0; d < D; ++d) {
-                        const float df = m - __ldcg(sf + (size_t)d * plane);
-                        sum += __expf(na4 * df * df);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) vv[j] = (d0 + j < D) ? __ldcg(sf + (size_t)(d0 + j) * plane) : 0.f;
-                }
-                // weight = 1 - 1/(D-1) * (sum - 1): separate roundings as in the reference so that flat-cost pixels
-                // (sum == D) give exactly 0 (monorec_model.py:258, :265-269)
-                const float w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
-                wsum += w;
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) acc[j] = fmaf(w, vv[j], acc[j]);
-            }
-            const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-                if (d0 + j < D) st_hint_f1(cv_out + (size_t)(d0 + j) * plane, (wsum == 0.f) ? 0.f : acc[j] * inv, pol_stream);
-        }
-    }
-#else
     // exp(-alpha (sad - min sad)^2) with sad = (1 - sv) / 2 is ex2(-(k (max sv - sv))^2), k = sqrt(alpha log2(e)) / 2
     const float kq = 0.5f * sqrtf(a.alpha * 1.4426950408889634f);
+    const size_t pstride = plane * sizeof(float);                    // bytes between the planes of a pixel
+    const size_t fstride = (size_t)a.B * D * pstride;                // bytes between the frames
+    float* wsm = reinterpret_cast<float*>(smem + L.ytile);           // D > kChunk: [F][kThreads] view weights (the tables are idle)
     for (int p = tid; p < TH * kTileCols && MR_CV_SKIP != 2; p += kThreads) {
         const int r = p >> 6, bc = p & 63;
         const int u = u0 + bc, v = v0 + r;
         const bool own = (bc >= 2) && (bc < 2 + kOutCols) && (u < W) && (v < H);
         if (!own) continue;
         const size_t pix = (size_t)v * W + u;
-        float* cv_out = a.cv + (size_t)b * D * plane + pix;
-        float* sf0 = a.sfcv + ((size_t)b * D) * plane + pix;       // frame f: + f * fstride
-        const size_t fstride = (size_t)a.B * D * plane;
+        char* cv_out = reinterpret_cast<char*>(a.cv + (size_t)b * D * plane + pix);
+        char* sf0 = reinterpret_cast<char*>(a.sfcv + ((size_t)b * D) * plane + pix);       // frame f: + f * fstride
         const unsigned char* vm = vmask + p;
         const int vstride = TH * kTileCols;
+        // addresses advance by pointer increments (one 64-bit add per access; an index expression costs a wide multiply each)
+        auto view_weight = [&](const float (&vv)[kChunk], const int n) {
+            float m4[4] = {-2.0f, -2.0f, -2.0f, -2.0f};
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) m4[j & 3] = fmaxf(m4[j & 3], (j < n) ? vv[j] : -2.0f);
+            const float km = kq * fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const float t = fmaf(-kq, vv[j], km);
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * t));
+                if (j < n) s4[j & 3] += e;
+            }
+            return (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        };
         if (D <= kChunk) {
-            // one pass: the planes of the next valid frame are requested before the current frame's arithmetic starts
-            float acc[kChunk], vv[kChunk], nx[kChunk];
+            float acc[kChunk], vv[kChunk];
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
             float wsum = 0.f;
-            for (int g = 0; g < F; ++g) {
-                if (vm[g * vstride] == 0) {   // invalid pixel of frame g: the whole plane stack is 0
-                    float* sf = sf0 + (size_t)g * fstride;
-                    for (int d = 0; d < D; ++d) sf[(size_t)d * plane] = 0.f;
+            char* sf = sf0;
+            for (int f = 0; f < F; ++f, sf += fstride) {
+                char* q = sf;
+                if (vm[f * vstride] == 0) {   // invalid pixel of frame f: the whole plane stack is 0
+                    for (int d = 0; d < D; ++d, q += pstride) *reinterpret_cast<float*>(q) = 0.f;
+                    continue;
                 }
-            }
-            int f = 0;
-            while (f < F && vm[f * vstride] == 0) ++f;   // first valid frame
-            if (f < F) {
-                const float* sf = sf0 + (size_t)f * fstride;
+                float sum;
+                if (D == kChunk) {            // every shipped configuration: no per-plane predicates
 #pragma unroll
-                for (int j = 0; j < kChunk; ++j) nx[j] = (j < D) ? __ldcg(sf + (size_t)j * plane) : -2.0f;
-            }
-            while (f < F) {
+                    for (int j = 0; j < kChunk; ++j, q += pstride) vv[j] = __ldcg(reinterpret_cast<const float*>(q));
+                    sum = view_weight(vv, kChunk);
+                } else {
 #pragma unroll
-                for (int j = 0; j < kChunk; ++j) vv[j] = nx[j];
-                int fn = f + 1;
-                while (fn < F && vm[fn * vstride] == 0) ++fn;
-                if (fn < F) {
-                    const float* sf = sf0 + (size_t)fn * fstride;
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) nx[j] = (j < D) ? __ldcg(sf + (size_t)j * plane) : -2.0f;
+                    for (int j = 0; j < kChunk; ++j, q += pstride) vv[j] = (j < D) ? __ldcg(reinterpret_cast<const float*>(q)) : -2.0f;
+                    sum = view_weight(vv, D);
                 }
-                float m4[4] = {-2.0f, -2.0f, -2.0f, -2.0f};
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) m4[j & 3] = fmaxf(m4[j & 3], vv[j]);
-                const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                const float km = kq * m;
-                float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) {
-                    const float t = fmaf(-kq, vv[j], km);
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * t));
-                    if (j < D) s4[j & 3] += e;
-                }
-                const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
                 // weight = 1 - 1/(D-1) * (sum - 1): separate roundings as in the reference so that flat-cost pixels
                 // (sum == D) give exactly 0 (monorec_model.py:258, :265-269)
                 const float w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
                 wsum += w;
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) acc[j] = fmaf(w, vv[j], acc[j]);
-                f = fn;
             }
             const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
+            char* q = cv_out;
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-                if (j < D) st_hint_f1(cv_out + (size_t)j * plane, acc[j] * inv, pol_stream);
+            for (int j = 0; j < kChunk; ++j, q += pstride)
+                if (j < D) st_hint_f1(reinterpret_cast<float*>(q), acc[j] * inv, pol_stream);
             continue;
         }
         // D > kChunk: view weights first (two passes over the L2-hot planes of each frame), then the fused volume in chunks
         float wsum = 0.f;
-        float* wsm = reinterpret_cast<float*>(smem + L.win);   // the windows are idle now: [F][kThreads] view weights
-        for (int f = 0; f < F; ++f) {
-            float* sf = sf0 + (size_t)f * fstride;
-            float w = 0.f;
-            if (vm[f * vstride] == 0) {
-                for (int d = 0; d < D; ++d) sf[(size_t)d * plane] = 0.f;
-            } else {
-                float m = -2.0f, sum = 0.f;
-                for (int d = 0; d < D; ++d) m = fmaxf(m, __ldcg(sf + (size_t)d * plane));
-                const float km = kq * m;
-                for (int d = 0; d < D; ++d) {
-                    const float t = fmaf(-kq, __ldcg(sf + (size_t)d * plane), km);
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * t));
-                    sum += e;
+        {
+            char* sf = sf0;
+            for (int f = 0; f < F; ++f, sf += fstride) {
+                float w = 0.f;
+                char* q = sf;
+                if (vm[f * vstride] == 0) {
+                    for (int d = 0; d < D; ++d, q += pstride) *reinterpret_cast<float*>(q) = 0.f;
+                } else {
+                    float m = -2.0f, sum = 0.f;
+                    for (int d = 0; d < D; ++d, q += pstride) m = fmaxf(m, __ldcg(reinterpret_cast<const float*>(q)));
+                    const float km = kq * m;
+                    q = sf;
+                    for (int d = 0; d < D; ++d, q += pstride) {
+                        const float t = fmaf(-kq, __ldcg(reinterpret_cast<const float*>(q)), km);
+                        float e;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * t));
+                        sum += e;
+                    }
+                    w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
                 }
-                w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
+                wsm[f * kThreads + tid] = w;
+                wsum += w;
             }
-            wsm[f * kThreads + tid] = w;
-            wsum += w;
         }
         const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
         for (int d0 = 0; d0 < D; d0 += kChunk) {
             float acc[kChunk];
 #pragma unroll
             for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
-            for (int f = 0; f < F; ++f) {
+            char* sf = sf0 + (size_t)d0 * pstride;
+            for (int f = 0; f < F; ++f, sf += fstride) {
                 const float w = wsm[f * kThreads + tid];
                 if (w == 0.f) continue;   // invalid (or weightless) frames add nothing
-                const float* sf = sf0 + (size_t)f * fstride;
+                char* q = sf;
 #pragma unroll
-                for (int j = 0; j < kChunk; ++j)
-                    if (d0 + j < D) acc[j] = fmaf(w, __ldcg(sf + (size_t)(d0 + j) * plane), acc[j]);
+                for (int j = 0; j < kChunk; ++j, q += pstride)
+                    if (d0 + j < D) acc[j] = fmaf(w, __ldcg(reinterpret_cast<const float*>(q)), acc[j]);
             }
+            char* q = cv_out + (size_t)d0 * pstride;
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-                if (d0 + j < D) st_hint_f1(cv_out + (size_t)(d0 + j) * plane, acc[j] * inv, pol_stream);
+            for (int j = 0; j < kChunk; ++j, q += pstride)
+                if (d0 + j < D) st_hint_f1(reinterpret_cast<float*>(q), acc[j] * inv, pol_stream);
         }
     }
-#endif
 }
 
 // ----------------------------------------------------------------------------------------------------------------
