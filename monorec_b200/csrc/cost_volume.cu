@@ -69,6 +69,7 @@ constexpr int kWinFloats = 3 * kChanStride;
 constexpr int kBoxRows = 8;                       // rows per TMA box
 constexpr int kMinGroup = MR_CV_MIN_GROUP;
 static_assert(kWinRows % kBoxRows == 0, "window rows must be a multiple of the TMA box height");
+static_assert(MR_MAX_FRAMES <= kWarps, "the plan gives every source frame its own warp");
 
 constexpr float kC1 = 0.01f * 0.01f;  // layers.py:116
 constexpr float kC2 = 0.03f * 0.03f;  // layers.py:117
@@ -545,12 +546,19 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
 
     // ---- keyframe tile (+0.5, monorec_model.py:232) and hoisted SSIM terms -------------------------------------
     const float* key = a.key + (size_t)b * 3 * plane;
-    for (int i = tid; i < 3 * (TH + 4) * 66; i += kThreads) {
-        int idx = i % 66, t = i / 66, rr = t % (TH + 4), ch = t / (TH + 4);
-        int u = u0 + idx - 1, v = v0 - 2 + rr;
-        float val = 0.f;
-        if (u >= 0 && u < W && v >= 0 && v < H) val = __ldg(key + ch * plane + (size_t)v * W + u) + 0.5f;
-        ytile[(rr * 3 + ch) * kRowStride + idx] = val;
+    for (int line = warp; line < 3 * (TH + 4); line += kWarps) {      // line = (tile row + 2) * 3 + channel
+        const int rr = line / 3, ch = line - 3 * rr;
+        const int v = v0 - 2 + rr;
+        const float* src = key + ch * plane + (size_t)v * W;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int idx = lane + 32 * k;
+            if (idx >= 66) break;
+            const int u = u0 + idx - 1;
+            float val = 0.f;
+            if (u >= 0 && u < W && v >= 0 && v < H) val = __ldg(src + u) + 0.5f;
+            ytile[line * kRowStride + idx] = val;
+        }
     }
     for (int i = tid; i < D; i += kThreads) zs[i] = __ldg(a.depths + i);
     if (lane < 6) {   // columns -1 and 64 of both row buffers stay zero
@@ -568,21 +576,24 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
     __syncthreads();
     // table entry for the column pair (2j, 2j+1) of e-row er, channel ch: (Y[2j], Y[2j+1], Sg[2j], Sg[2j+1]) with
     // Y = 9 mu_y = sum y, Sg = 81 (sigma_y + C2) = 9 sum y^2 - Y^2 + 81 C2
-    for (int i = tid; i < 3 * (TH + 2) * kTileCols; i += kThreads) {
-        int bc = i % kTileCols, t = i / kTileCols, er = t % (TH + 2), ch = t / (TH + 2);
-        const float* y = ytile + (er * 3 + ch) * kRowStride + bc;  // rows er..er+2, idx bc..bc+2
-        float s1 = 0.f, s2 = 0.f;
+    for (int line = warp; line < 3 * (TH + 2); line += kWarps) {      // line = e-row * 3 + channel
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+        for (int k = 0; k < 2; ++k) {
+            const int bc = lane + 32 * k;
+            const float* y = ytile + line * kRowStride + bc;  // rows er..er+2 of this channel, idx bc..bc+2
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                float q = y[dy * 3 * kRowStride + dx];
-                s1 += q;
-                s2 = fmaf(q, q, s2);
-            }
-        float* dst = cst + ((er * 3 + ch) * (kTileCols / 2) + (bc >> 1)) * 4 + (bc & 1);
-        dst[0] = s1;
-        dst[2] = fmaf(9.0f, s2, -s1 * s1) + 81.0f * kC2;
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    float q = y[dy * 3 * kRowStride + dx];
+                    s1 += q;
+                    s2 = fmaf(q, q, s2);
+                }
+            float* dst = cst + (line * (kTileCols / 2) + (bc >> 1)) * 4 + (bc & 1);
+            dst[0] = s1;
+            dst[2] = fmaf(9.0f, s2, -s1 * s1) + 81.0f * kC2;
+        }
     }
 
     const float fW = (float)W, fH = (float)H;
@@ -594,8 +605,8 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
     //      The D samples of a pixel lie on one line and move monotonically with the depth while the denominator keeps
     //      its sign, so the farthest and the nearest plane decide. -----------------------------------------------------
     for (int q = tid; q < F * TH * kTileCols; q += kThreads) {
-        const int f = q / (TH * kTileCols), p = q - f * (TH * kTileCols);
-        const int r = p >> 6, bc = p & 63;
+        const int fr = q >> 6, bc = q & 63;            // fr = f * TH + r
+        const int f = fr / TH, r = fr - f * TH;
         const int u = u0 + bc, v = v0 + r;
         bool ok = (bc >= 2) && (bc < 2 + kOutCols) && (u >= 2) && (u < W - 2) && (v >= 2) && (v < H - 2);
         if (ok) {
@@ -616,7 +627,8 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
             }
         }
         vmask[q] = ok ? 1 : 0;
-        if (ok) { atomicMin(&rowrng[2 * f], r); atomicMax(&rowrng[2 * f + 1], r); }
+        // (a warp covers half a tile row of one frame: one pair of shared-memory atomics per warp, not per pixel)
+        if (__any_sync(0xffffffffu, ok) && lane == 0) { atomicMin(&rowrng[2 * f], r); atomicMax(&rowrng[2 * f + 1], r); }
     }
     __syncthreads();
 
@@ -663,9 +675,9 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
         gid[u] = 0xFFFF;
     }
     __syncthreads();
-    if (tid < F) {
+    if (lane == 0 && warp < F) {   // one frame per warp: the F serial scans run side by side instead of as divergent lanes
         // greedy runs of consecutive planes whose union still fits one window
-        const int f = tid;
+        const int f = warp;
         int ng = 0;
         const int rlo = rowrng[2 * f], rhi = rowrng[2 * f + 1];
         if (rhi >= rlo && a.use_tma) {
@@ -696,14 +708,15 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
         nwin[f] = ng;
     }
     __syncthreads();
-    if (tid < F) {
+    if (lane == 0 && warp < F) {
+        const int f = warp;
         int base = 0;
-        for (int k = 0; k < tid; ++k) base += nwin[k];
-        for (int g = 0; g < nwin[tid]; ++g) {
-            ginfo[tid * D + g].seq = (short)(base + g);
-            seq2g[base + g] = (unsigned short)(tid * D + g);
+        for (int k = 0; k < f; ++k) base += nwin[k];
+        for (int g = 0; g < nwin[f]; ++g) {
+            ginfo[f * D + g].seq = (short)(base + g);
+            seq2g[base + g] = (unsigned short)(f * D + g);
         }
-        if (tid == F - 1) ctr[1] = base + nwin[tid];
+        if (f == F - 1) ctr[1] = base + nwin[f];
     }
     __syncthreads();
 
