@@ -85,6 +85,14 @@ int mr_cost_volume_fwd_gather(const float* keyframe, const float* const* frames,
                               int B, int F, int D, int H, int W,
                               float alpha, const float* chan_w, void* stream);
 
+/* mr_cost_volume_fwd that additionally writes the single-frame volumes in the convolution engine's input layout,
+ * out_sfcv_nhwc [F,B,H,W,D] as fp32 (MR_DT_F32) or IEEE half (MR_DT_F16), from the registers of the kernel's per-pixel phase
+ * (replaces F layout-change launches in front of the MaskModule, monorec_model.py:357-365).  Needs D <= 32 and D % 8 == 0. */
+int mr_cost_volume_fwd_nhwc(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
+                            float* out_cv, float* out_sfcv, void* out_sfcv_nhwc, int nhwc_dtype,
+                            int B, int F, int D, int H, int W,
+                            float alpha, const float* chan_w, void* stream);
+
 /* Same path with HOST buffers (pinned or pageable): uploads the images and matrices, runs
  * mr_projection_tables + mr_cost_volume_fwd and downloads both volumes; batch elements are pipelined on
  * internal streams so copies overlap the kernel.  This is the end-to-end entry bench.py times as `e2e`.

@@ -94,9 +94,18 @@ class CostVolumeModule(nn.Module):
                 cw = (_lib.c_float * 3)(*self.channel_weights)
             else:
                 cw = (_lib.c_float * 3)(1 / 3, 1 / 3, 1 / 3)  # monorec_model.py:174-177
-            fwd = lib.mr_cost_volume_fwd if self.tma_windows else lib.mr_cost_volume_fwd_gather
-            _lib.check(fwd(keyframe.data_ptr(), _lib.ptr_array(frames), proj.data_ptr(), depths.data_ptr(), cv.data_ptr(),
-                           sfcv.data_ptr(), B, F, D, H, W, float(self.alpha), cw, stream), "mr_cost_volume_fwd")
+            nhwc = data_dict.get("_sfcv_nhwc")   # MonoRecModel: the MaskModule's input buffer [F*B,H,W,D], filled by the kernel
+            if nhwc is not None and self.tma_windows and D <= 32 and D % 8 == 0 and tuple(nhwc.shape) == (F * B, H, W, D) \
+                    and nhwc.is_contiguous() and nhwc.dtype in (torch.float32, torch.float16):
+                _lib.check(lib.mr_cost_volume_fwd_nhwc(keyframe.data_ptr(), _lib.ptr_array(frames), proj.data_ptr(),
+                                                       depths.data_ptr(), cv.data_ptr(), sfcv.data_ptr(), nhwc.data_ptr(),
+                                                       1 if nhwc.dtype == torch.float16 else 0, B, F, D, H, W,
+                                                       float(self.alpha), cw, stream), "mr_cost_volume_fwd_nhwc")
+                data_dict["_sfcv_nhwc_filled"] = True
+            else:
+                fwd = lib.mr_cost_volume_fwd if self.tma_windows else lib.mr_cost_volume_fwd_gather
+                _lib.check(fwd(keyframe.data_ptr(), _lib.ptr_array(frames), proj.data_ptr(), depths.data_ptr(), cv.data_ptr(),
+                               sfcv.data_ptr(), B, F, D, H, W, float(self.alpha), cw, stream), "mr_cost_volume_fwd")
         data_dict["cost_volume"] = cv
         data_dict["single_frame_cvs"] = [sfcv[f] for f in range(F)]
         # host-side issue time (the reference's number includes its device work only because it synchronises implicitly)

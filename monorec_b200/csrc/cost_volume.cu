@@ -30,6 +30,7 @@
 // one pixel lie on a line, monotone in depth, so the extremes decide) and whole row ranges / frames of a tile are skipped.
 #include "mr_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <type_traits>
 
@@ -84,6 +85,8 @@ struct CvArgs {
     const float* depths;                 // [D]
     float* cv;                           // [B,D,H,W]
     float* sfcv;                         // [F,B,D,H,W]
+    void* sf_nhwc;                       // optional [F,B,H,W,D] copy of sfcv for the conv engine (D <= 32, D % 8 == 0) or nullptr
+    int sf_nhwc_half;                    // 1: that copy is IEEE half, 0: fp32
     int B, F, D, H, W, TH, b0;
     int use_tma;                         // 0: every unit gathers from global memory
     float alpha, inv_dm1;
@@ -857,8 +860,13 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
             char* sf = sf0;
             for (int f = 0; f < F; ++f, sf += fstride) {
                 char* q = sf;
+                char* nh = nullptr;           // this pixel's D channels of frame f in the NHWC copy
+                if (a.sf_nhwc != nullptr)
+                    nh = static_cast<char*>(a.sf_nhwc) + (((size_t)f * a.B + b) * plane + pix) * D * (a.sf_nhwc_half ? 2 : 4);
                 if (vm[f * vstride] == 0) {   // invalid pixel of frame f: the whole plane stack is 0
                     for (int d = 0; d < D; ++d, q += pstride) *reinterpret_cast<float*>(q) = 0.f;
+                    if (nh != nullptr)
+                        for (int o = 0; o < D * (a.sf_nhwc_half ? 2 : 4); o += 16) *reinterpret_cast<uint4*>(nh + o) = make_uint4(0, 0, 0, 0);
                     continue;
                 }
                 float sum;
@@ -877,6 +885,25 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
                 wsum += w;
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) acc[j] = fmaf(w, vv[j], acc[j]);
+                if (nh != nullptr) {          // the MaskModule's input layout, written while the values are in registers
+                    if (a.sf_nhwc_half) {
+#pragma unroll
+                        for (int j = 0; j < kChunk; j += 8) {
+                            if (j >= D) break;
+                            uint4 pk;
+                            __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(vv[j + 2 * k], vv[j + 2 * k + 1]);
+                            *reinterpret_cast<uint4*>(nh + 2 * j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kChunk; j += 4) {
+                            if (j >= D) break;
+                            *reinterpret_cast<float4*>(nh + 4 * j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+                        }
+                    }
+                }
             }
             const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
             char* q = cv_out;
@@ -1059,7 +1086,7 @@ extern "C" int mr_projection_tables(const float* keyframe_pose, const float* key
 int mr::launch_cost_volume(const float* keyframe, const float* const* frames, const float* proj,
                            const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H, int W,
                            float alpha, const float* chan_w, int b_begin, int b_count, int gather_only,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, void* sf_nhwc, int sf_nhwc_dtype) {
     MR_REQUIRE(keyframe && frames && proj && depths && out_cv && out_sfcv, "mr_cost_volume_fwd: null pointer");
     MR_REQUIRE(b_begin >= 0 && b_count >= 1 && b_begin + b_count <= B, "mr_cost_volume_fwd: bad batch range");
     MR_REQUIRE(B >= 1 && B <= 21845, "mr_cost_volume_fwd: batch %d out of range", B);
@@ -1073,6 +1100,10 @@ int mr::launch_cost_volume(const float* keyframe, const float* const* frames, co
         a.frames[f] = frames[f];
     }
     a.proj = proj; a.depths = depths; a.cv = out_cv; a.sfcv = out_sfcv;
+    MR_REQUIRE(sf_nhwc == nullptr || (D <= kChunk && (D % 8) == 0 && (reinterpret_cast<uintptr_t>(sf_nhwc) & 15) == 0 &&
+                                      (sf_nhwc_dtype == MR_DT_F32 || sf_nhwc_dtype == MR_DT_F16)),
+               "mr_cost_volume_fwd_nhwc: the NHWC copy needs D <= %d, D %% 8 == 0, a 16-byte aligned buffer and an fp32 / half type", kChunk);
+    a.sf_nhwc = sf_nhwc; a.sf_nhwc_half = (sf_nhwc_dtype == MR_DT_F16) ? 1 : 0;
     a.B = B; a.F = F; a.D = D; a.H = H; a.W = W; a.b0 = b_begin;
     // TMA addresses the frames as (W, H, 3B) tensors: the row pitch must be a multiple of 16 bytes and the base 16-byte
     // aligned; otherwise (ragged widths) every unit takes the global gather of the same kernel.
@@ -1118,30 +1149,24 @@ int mr::launch_cost_volume(const float* keyframe, const float* const* frames, co
     return MR_OK;
 }
 
-extern "C" long long mr_cost_volume_workspace_bytes(int B, int F, int H, int W) {
-    (void)B; (void)F; (void)H; (void)W;
-    return 0;   // since 0.2 the kernel stages source windows by TMA from the frames themselves: no re-laid copy is needed
-}
-
-extern "C" int mr_cost_volume_fwd_ws(const float* keyframe, const float* const* frames, const float* proj,
-                                     const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H, int W,
-                                     float alpha, const float* chan_w, void* workspace, long long workspace_bytes,
-                                     void* stream) {
-    (void)workspace; (void)workspace_bytes;
-    return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0, B, 0,
-                                  (cudaStream_t)stream);
-}
-
 extern "C" int mr_cost_volume_fwd(const float* keyframe, const float* const* frames, const float* proj,
                                   const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H,
                                   int W, float alpha, const float* chan_w, void* stream) {
     return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0,
-                                  B, 0, (cudaStream_t)stream);
+                                  B, 0, (cudaStream_t)stream, nullptr, 0);
 }
 
 extern "C" int mr_cost_volume_fwd_gather(const float* keyframe, const float* const* frames, const float* proj,
                                          const float* depths, float* out_cv, float* out_sfcv, int B, int F, int D, int H,
                                          int W, float alpha, const float* chan_w, void* stream) {
     return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0,
-                                  B, 1, (cudaStream_t)stream);
+                                  B, 1, (cudaStream_t)stream, nullptr, 0);
+}
+
+extern "C" int mr_cost_volume_fwd_nhwc(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
+                                       float* out_cv, float* out_sfcv, void* out_sfcv_nhwc, int nhwc_dtype, int B, int F, int D,
+                                       int H, int W, float alpha, const float* chan_w, void* stream) {
+    MR_REQUIRE(out_sfcv_nhwc != nullptr, "mr_cost_volume_fwd_nhwc: null NHWC buffer");
+    return mr::launch_cost_volume(keyframe, frames, proj, depths, out_cv, out_sfcv, B, F, D, H, W, alpha, chan_w, 0, B, 0,
+                                  (cudaStream_t)stream, out_sfcv_nhwc, nhwc_dtype);
 }

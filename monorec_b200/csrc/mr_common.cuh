@@ -13,7 +13,8 @@ void count_launch(int n = 1);
 // cost_volume.cu: launches the fused kernel for batch elements [b_begin, b_begin + b_count) of a B-element problem
 int launch_cost_volume(const float* keyframe, const float* const* frames, const float* proj, const float* depths,
                        float* out_cv, float* out_sfcv, int B, int F, int D, int H, int W, float alpha,
-                       const float* chan_w, int b_begin, int b_count, int gather_only, cudaStream_t stream);
+                       const float* chan_w, int b_begin, int b_count, int gather_only, cudaStream_t stream,
+                       void* sf_nhwc = nullptr, int sf_nhwc_dtype = 0);
 
 inline int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return MR_OK;

@@ -234,9 +234,12 @@ class MaskModule(nn.Module):
         nF = len(sfcvs)
         B, D, H, W = sfcvs[0].shape
         # all frames go through the encoder as one batch of F*B volumes (the reference loops, :357-365)
-        x = torch.empty(nF * B, H, W, D, device=sfcvs[0].device, dtype=C.act_dtype())
-        for f, v in enumerate(sfcvs):
-            C.nchw_to_nhwc(v.to(torch.float32), out=x[f * B:(f + 1) * B])
+        x = data_dict.pop("_sfcv_nhwc", None) if data_dict.pop("_sfcv_nhwc_filled", False) else None
+        if x is None or x.dtype != C.act_dtype() or tuple(x.shape) != (nF * B, H, W, D):
+            # (standalone call, or a configuration the fused kernel does not write the engine layout for)
+            x = torch.empty(nF * B, H, W, D, device=sfcvs[0].device, dtype=C.act_dtype())
+            for f, v in enumerate(sfcvs):
+                C.nchw_to_nhwc(v.to(torch.float32), out=x[f * B:(f + 1) * B])
         if not self.use_cv:
             x.zero_()
         cv_feats = []
@@ -479,6 +482,12 @@ class MonoRecModel(nn.Module):
 
         with torch.no_grad():
             if not self.no_cv:
+                if hasattr(self, "att_module") and self.att_module.use_cv and C.MODE in ("tf32", "f16") \
+                        and self.cv_depth_steps <= 32 and self.cv_depth_steps % 8 == 0:
+                    # the MaskModule's NHWC input is written by the cost-volume kernel's per-pixel phase (no layout-change launches)
+                    nf = (len(data_dict["frames"]) if self.use_mono else 0) + (1 if self.use_stereo else 0)
+                    data_dict["_sfcv_nhwc"] = torch.empty(nf * keyframe.shape[0], keyframe.shape[2], keyframe.shape[3],
+                                                          self.cv_depth_steps, device=keyframe.device, dtype=C.act_dtype())
                 data_dict = self.cv_module(data_dict)
             else:
                 s = list(keyframe.shape)
@@ -524,6 +533,8 @@ class MonoRecModel(nn.Module):
             data_dict["result"] = data_dict["predicted_inverse_depths"][0]
             data_dict["mask"] = data_dict["cv_mask"]
         data_dict.pop("_cv_range", None)
+        data_dict.pop("_sfcv_nhwc", None)
+        data_dict.pop("_sfcv_nhwc_filled", None)
         return data_dict
 
 

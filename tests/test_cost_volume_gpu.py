@@ -222,3 +222,22 @@ def test_cost_volume_golden_d64_f6():
     data, D, ref_cv, ref_sf = synth_small_dict("d")
     cv, sf = _run(data, steps=D)
     print(compare_volumes(cv, sf, ref_cv, ref_sf))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_nhwc_copy_of_single_frame_volumes(dtype):
+    """mr_cost_volume_fwd_nhwc: the engine-layout copy written by the per-pixel phase == the NCHW volumes permuted (and
+    rounded to half), bit for bit, invalid pixels included."""
+    from monorec_b200.cost_volume import CostVolumeModule
+    from monorec_b200.synthetic import make_inputs, to_device
+    B, F, H, W, D = 2, 3, 64, 128, 32
+    d = to_device(make_inputs(B, F, H, W, seed=77), "cuda:0")
+    d["_cv_range"] = (0.0025, 0.33, D)
+    d["_sfcv_nhwc"] = torch.full((F * B, H, W, D), 7.0, device="cuda:0", dtype=dtype)
+    out = CostVolumeModule()(d)
+    torch.cuda.synchronize()
+    assert out.get("_sfcv_nhwc_filled") is True
+    ref = torch.cat([s.permute(0, 2, 3, 1) for s in out["single_frame_cvs"]], 0).to(dtype)
+    assert torch.equal(out["_sfcv_nhwc"], ref)
+    # the ring of invalid border pixels is zero in both
+    assert float(out["_sfcv_nhwc"][:, :2].abs().max()) == 0.0
