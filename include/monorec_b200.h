@@ -200,6 +200,27 @@ int mr_max_over_frames(const float* src, float* dst, int F, long long n_per_fram
 /* out[b,d,p] = volume[b,d,p] * (1 - mask[b,p])   (monorec_model.py:713, NCHW volume [B,D,HW], mask [B,HW]). */
 int mr_mask_volume(const float* volume, const float* mask, float* out, int B, int D, int HW, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Evaluation-side helpers.
+ *
+ * mr_sparse_metrics: the seven sparse depth metrics of model/metric_functions/sparse_metrics.py:81-251 (a1, a2, a3, rmse,
+ * rmse_log, abs_rel, sq_rel with utils/util.py:36-65, :101-118) in one pass; evaluater/evaluater.py:78-112 calls the seven
+ * reference functions (~12 elementwise torch kernels each) one after the other.
+ *   result, target   [B,1,H,W] predicted / ground-truth INVERSE depth (target 0 = no measurement)
+ *   mvobj_mask       [B,1,H,W] or NULL: with it, pixels whose mask is <= 0.5 are excluded (the *_onlydynamic variants)
+ *   roi              host int[4] {r0, r1, c0, c1} (python slice semantics) or NULL; max_distance <= 0: no clamp
+ *   pred_all_valid   0: pixels with result == 0 are excluded (the *_onlyvalid variants)
+ *   out_metrics      device float[7]: a1, a2, a3, rmse, rmse_log, abs_rel, sq_rel; no host synchronisation
+ *   workspace        device buffer of mr_sparse_metrics_workspace(B) bytes, 8-byte aligned
+ * mr_images_u8_to_f32: uint8 HWC images [B,Hs,Ws,3] -> float CHW [B,3,H,W] = u / 255 - 0.5 of the crop starting at
+ * (crop_top, crop_left) (data_loader/kitti_odometry_dataset.py:121-132 without the PIL resize). */
+long long mr_sparse_metrics_workspace(int B);
+int mr_sparse_metrics(const float* result, const float* target, const float* mvobj_mask, int B, int H, int W,
+                      const int* roi, float max_distance, int pred_all_valid, float* out_metrics,
+                      void* workspace, long long workspace_bytes, void* stream);
+int mr_images_u8_to_f32(const unsigned char* src, float* dst, int B, int Hs, int Ws, int crop_top, int crop_left,
+                        int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

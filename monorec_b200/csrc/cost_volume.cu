@@ -1107,8 +1107,7 @@ int mr::launch_cost_volume(const float* keyframe, const float* const* frames, co
     a.B = B; a.F = F; a.D = D; a.H = H; a.W = W; a.b0 = b_begin;
     // TMA addresses the frames as (W, H, 3B) tensors: the row pitch must be a multiple of 16 bytes and the base 16-byte
     // aligned; otherwise (ragged widths) every unit takes the global gather of the same kernel.
-    static CvMaps maps;   // storage for the by-value kernel parameter; rebuilt on every call before the launch reads it
-    CvMaps local{};
+    CvMaps local{};       // by-value kernel parameter (__grid_constant__): one tensor map per source frame
     a.use_tma = 0;
     EncodeTiledFn encode = gather_only ? nullptr : get_encode_fn();
     if (encode != nullptr && (W % 4) == 0) {
@@ -1129,7 +1128,6 @@ int mr::launch_cost_volume(const float* keyframe, const float* const* frames, co
             a.use_tma = 1;
         }
     }
-    (void)maps;
     a.TH = pick_tile_rows(D, F, a.use_tma);
     MR_REQUIRE(a.TH > 0, "mr_cost_volume_fwd: no tile height fits shared memory for D=%d F=%d", D, F);
     a.alpha = alpha;

@@ -15,9 +15,12 @@ Files written
                           valid masks, per-plane float64 checksums)
   cv_synth_small.npz      full reference cost-volume tensors for small seeded synthetic configs
   cv_synth_d64f6.npz      the same for 64 planes x 6 source frames (`--only-d64f6`)
+  cv_config2.npz          BASELINE config 2's geometry at full size (256x512, 32 planes, 4 source frames, seed 100 of the
+                          synthetic generator): sub-sampled volumes, rows, arg-max, validity, checksums (`--only-config2`)
   model_kitti_sample.npz  full MonoRecModel forward on the bundled KITTI sample, seeded weights (`--only-kitti-model`)
   model_synth_small.npz   full MonoRecModel forward (seeded weights, 2 gains) on a small synthetic config:
                           cv_mask, 4 depth maps, image_features checksums
+  metrics.npz             the reference's seven sparse depth metrics on seeded inputs, four parameter sets (`--only-metrics`)
   model_fp64.npz          the same two model configurations evaluated by the reference in float64 (`--only-model-fp64`):
                           the reference's own fp32 rounding noise on `result` / `cv_mask`, which sizes the GPU gates
 """
@@ -192,6 +195,50 @@ def main():
                 out[f"{cfg}_{gain_tag}_cv_mask64"] = r64["cv_mask"].float().numpy().astype(np.float16)
                 print(cfg, gain_tag, "reference fp32 vs fp64: result", d_res, "mask", d_mask, "heads", d_heads, flush=True)
         np.savez_compressed(HERE / "model_fp64.npz", **out)
+        return
+    if "--only-config2" in sys.argv:
+        # BASELINE config 2's geometry at full size (256x512, 32 planes, 4 source frames, one keyframe of the synthetic
+        # KITTI-shaped generator bench.py uses): sub-sampled volumes, rows, full arg-max / validity maps and per-plane
+        # checksums, like kitti_sample.npz
+        d = make_inputs(1, 4, 256, 512, seed=100)
+        cv, sf = run_ref_cv(ref_mod, d)
+        sub = (slice(None), slice(None), slice(2, None, 4), slice(1, None, 8))
+        np.savez_compressed(
+            HERE / "cv_config2.npz", cfg=np.array([1, 4, 32, 256, 512, 100]),
+            cv_sub=cv[sub].numpy(), sf_sub=np.stack([v[sub].numpy() for v in sf]),
+            cv_rows=cv[:, :, 100:104].numpy(), sf_rows=np.stack([v[:, :, 100:104].numpy() for v in sf]),
+            argmax=cv.argmax(1).numpy().astype(np.uint8), margin=top2_margin(cv).numpy().astype(np.float16),
+            cv_zero=np.packbits((cv == 0).all(1).numpy()),
+            sf_zero=np.packbits(np.stack([(v == 0).all(1).numpy() for v in sf])),
+            cv_plane_sum=cv.double().sum((2, 3)).numpy(), sf_plane_sum=np.stack([v.double().sum((2, 3)).numpy() for v in sf]))
+        print("config 2 golden: valid share per frame", [float(1 - (v == 0).all(1).float().mean()) for v in sf])
+        return
+    if "--only-metrics" in sys.argv:
+        # the reference's own sparse metric functions (model/metric_functions/sparse_metrics.py) on small seeded inputs:
+        # inverse-depth predictions, LiDAR-like sparse targets (~8 % of the pixels), a moving-object mask
+        sys.path.insert(0, str(REF))
+        sys.modules.setdefault("kornia.geometry.camera", types.ModuleType("kornia.geometry.camera"))
+        import model.metric_functions.sparse_metrics as SM  # noqa
+        g = torch.Generator().manual_seed(11)
+        B, H, W = 3, 48, 80
+        pred = torch.rand(B, 1, H, W, generator=g) * 0.3 + 0.002
+        pred[torch.rand(B, 1, H, W, generator=g) < 0.02] = 0.0                      # predictions that are exactly 0
+        gt = (pred * (1 + 0.25 * torch.randn(B, 1, H, W, generator=g))).clamp_min(1e-3)
+        gt[torch.rand(B, 1, H, W, generator=g) > 0.08] = 0.0                        # sparse
+        mv = (torch.rand(B, 1, H, W, generator=g) > 0.6).float()
+        out = {"pred": pred.numpy(), "gt": gt.numpy(), "mvobj": mv.numpy()}
+        names = ("a1", "a2", "a3", "rmse", "rmse_log", "abs_rel", "sq_rel")
+        cases = {"plain": dict(), "roi_md": dict(roi=[4, 44, 8, 72], max_distance=80.0),
+                 "onlyvalid": dict(roi=None, max_distance=50.0, pred_all_valid=False),
+                 "onlydynamic": dict(roi=None, max_distance=80.0, use_cvmask=True)}   # (the reference does not crop mvobj_mask: roi must be None)
+        for tag, kw in cases.items():
+            vals = []
+            for n in names:
+                d = {"result": pred.clone(), "target": gt.clone(), "mvobj_mask": mv.clone()}
+                vals.append(float(getattr(SM, f"{n}_sparse_metric")(d, **kw)))
+            out[f"case_{tag}"] = np.array(vals, dtype=np.float64)
+            print(tag, dict(zip(names, vals)))
+        np.savez_compressed(HERE / "metrics.npz", **out)
         return
     if "--only-d64f6" in sys.argv:
         # BASELINE config 5's plane and frame counts (64 planes, 6 source frames) at a small size; added after the other

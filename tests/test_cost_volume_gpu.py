@@ -241,3 +241,38 @@ def test_nhwc_copy_of_single_frame_volumes(dtype):
     assert torch.equal(out["_sfcv_nhwc"], ref)
     # the ring of invalid border pixels is zero in both
     assert float(out["_sfcv_nhwc"][:, :2].abs().max()) == 0.0
+
+
+def test_golden_config2_full_size():
+    """BASELINE config 2's geometry at full size (256x512, D=32, F=4; tests/golden/cv_config2.npz from the unmodified reference):
+    sub-sampled volumes and full rows within 1e-3, validity maps (valid shares 96 / 53 / 97 / 22 % per frame), arg-max under the
+    tie rule, per-plane checksums."""
+    from monorec_b200.synthetic import make_inputs
+    from tests.helpers import GOLDEN, compare_volumes
+    g = np.load(GOLDEN / "cv_config2.npz")
+    B, nF, D, H, W, seed = [int(v) for v in g["cfg"]]
+    cv, sf = _run(make_inputs(B, nF, H, W, seed=seed), steps=D)
+    sub = (slice(None), slice(None), slice(2, None, 4), slice(1, None, 8))
+    stats = compare_volumes(cv[sub], [s[sub] for s in sf], torch.from_numpy(g["cv_sub"]), [torch.from_numpy(v) for v in g["sf_sub"]])
+    rows = (slice(None), slice(None), slice(100, 104))
+    stats_rows = compare_volumes(cv[rows], [s[rows] for s in sf], torch.from_numpy(g["cv_rows"]), [torch.from_numpy(v) for v in g["sf_rows"]])
+    ref_sf_zero = np.unpackbits(g["sf_zero"])[: nF * H * W].reshape(nF, 1, H, W).astype(bool)
+    masks_agree = torch.ones(1, H, W, dtype=torch.bool)
+    flips = 0
+    for f in range(nF):
+        mz, rz = (sf[f] == 0).all(1), torch.from_numpy(ref_sf_zero[f])
+        masks_agree &= (mz == rz)
+        flips += int((mz != rz).sum())
+    assert flips <= 4 * nF, f"{flips} validity flips"
+    ref_zero = torch.from_numpy(np.unpackbits(g["cv_zero"])[: H * W].reshape(1, H, W).astype(bool))
+    both = (~ref_zero) & (~(cv == 0).all(1)) & masks_agree
+    same = cv.argmax(1) == torch.from_numpy(g["argmax"].astype(np.int64))
+    margin = torch.from_numpy(g["margin"].astype(np.float32))
+    agree3 = same[both & (margin > 1e-3)].float().mean().item()
+    agree4 = same[both & (margin > 1e-4)].float().mean().item()
+    print("config 2", stats, stats_rows, "argmax margin>1e-3", agree3, "margin>1e-4", agree4, "raw", same[both].float().mean().item(),
+          "validity flips", flips)
+    assert agree3 == 1.0 and agree4 > 0.9999
+    np.testing.assert_allclose(cv.double().sum((2, 3)).numpy(), g["cv_plane_sum"], rtol=0, atol=1e-4 * H * W)
+    for f in range(nF):
+        np.testing.assert_allclose(sf[f].double().sum((2, 3)).numpy(), g["sf_plane_sum"][f], rtol=0, atol=1e-4 * H * W)
