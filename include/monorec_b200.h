@@ -221,6 +221,29 @@ int mr_sparse_metrics(const float* result, const float* target, const float* mvo
 int mr_images_u8_to_f32(const unsigned char* src, float* dst, int B, int Hs, int Ws, int crop_top, int crop_left,
                         int H, int W, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Point-cloud side: create_pointcloud.py:65-105 + utils/ply_utils.py:34-53 on the device.
+ *
+ * mr_pointcloud_keep_mask: keep[b,p] = 1 iff no pixel with cv_mask >= thresh lies in the (mask_fill+1)^2 window around p
+ *   (create_pointcloud.py:77-78 with mask_fill = 32, thresh = 0.1); cv_mask, keep: [B,1,H,W].
+ * mr_pointcloud_add: PLYSaver.add_depthmap with the sliding-window vote folded in.  Appends the vertices (x, y, z, r, g, b)
+ *   of a batch to a device buffer, in the reference's order (batch element, then pixel), without host synchronisation.
+ *   inv_depth [B,1,H,W] (data_dict["result"]); keyframe [B,3,H,W]; K, pose [B,4,4];
+ *   keep_masks: host array of n_masks device pointers [B,1,H,W] (the window's keep masks) -- a pixel survives iff more than
+ *     n_masks - min_hits of them are 1 (create_pointcloud.py:93-95); n_masks = 0: no vote;
+ *   min_d / max_d: distance range; roi: host int[4] {r0, r1, c0, c1} or NULL; dropout_rand: [B,1,H,W] uniform numbers (a
+ *     vertex is kept iff rand > dropout; torch.rand_like in the reference) or NULL;
+ *   vertices: device float [capacity][6]; n_before: vertices already stored; n_after: DEVICE long long, the new count, or
+ *     minus the needed count if the buffer is too small (then nothing is written);
+ *   workspace: device buffer of mr_pointcloud_workspace(B,H,W) bytes. */
+int mr_pointcloud_keep_mask(const float* cv_mask, float* keep, int B, int H, int W, int mask_fill, float thresh, void* stream);
+long long mr_pointcloud_workspace(int B, int H, int W);
+int mr_pointcloud_add(const float* inv_depth, const float* keyframe, const float* K, const float* pose,
+                      const float* const* keep_masks, int n_masks, int min_hits, int B, int H, int W,
+                      float min_d, float max_d, const int* roi, const float* dropout_rand, float dropout,
+                      float* vertices, long long capacity, long long n_before, long long* n_after,
+                      void* workspace, long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ Files written
   model_kitti_sample.npz  full MonoRecModel forward on the bundled KITTI sample, seeded weights (`--only-kitti-model`)
   model_synth_small.npz   full MonoRecModel forward (seeded weights, 2 gains) on a small synthetic config:
                           cv_mask, 4 depth maps, image_features checksums
+  pointcloud.npz          the reference's PLYSaver.add_depthmap + mask dilation / vote on seeded inputs (`--only-pointcloud`)
   metrics.npz             the reference's seven sparse depth metrics on seeded inputs, four parameter sets (`--only-metrics`)
   model_fp64.npz          the same two model configurations evaluated by the reference in float64 (`--only-model-fp64`):
                           the reference's own fp32 rounding noise on `result` / `cv_mask`, which sizes the GPU gates
@@ -239,6 +240,41 @@ def main():
             out[f"case_{tag}"] = np.array(vals, dtype=np.float64)
             print(tag, dict(zip(names, vals)))
         np.savez_compressed(HERE / "metrics.npz", **out)
+        return
+    if "--only-pointcloud" in sys.argv:
+        # the unmodified PLYSaver (utils/ply_utils.py) + the mask lines of create_pointcloud.py:77-78, :93-95 on seeded inputs
+        import torch.nn.functional as F
+        sys.path.insert(0, str(REF))
+        from utils.ply_utils import PLYSaver  # noqa
+        g = torch.Generator().manual_seed(23)
+        B, H, W, NW = 2, 40, 64, 5
+        inv_depth = torch.rand(B, 1, H, W, generator=g) * 0.3 + 0.002
+        image = torch.rand(B, 3, H, W, generator=g) - 0.5
+        K = torch.eye(4).repeat(B, 1, 1)
+        K[:, 0, 0] = 61.0; K[:, 1, 1] = 60.0; K[:, 0, 2] = 31.0; K[:, 1, 2] = 19.5
+        ang = torch.tensor([0.05, -0.08])
+        pose = torch.eye(4).repeat(B, 1, 1)
+        pose[:, 0, 0] = ang.cos(); pose[:, 0, 2] = ang.sin(); pose[:, 2, 0] = -ang.sin(); pose[:, 2, 2] = ang.cos()
+        pose[:, :3, 3] = torch.tensor([[1.0, -0.2, 12.0], [3.0, 0.1, 14.5]])
+        cv_masks = [torch.rand(B, 1, H, W, generator=g) * 0.09 for _ in range(NW)]          # below the 0.1 threshold ...
+        cv_masks[0][0, 0, 3, 5] = 0.5; cv_masks[2][1, 0, 30, 50] = 0.11; cv_masks[4][0, 0, 39, 63] = 0.1   # ... except three hits
+        keeps = []
+        for m in cv_masks:                                                                   # create_pointcloud.py:77-78
+            mask = (m >= .1).to(dtype=torch.float32)
+            keeps.append((F.conv2d(mask, mask.new_ones((1, 1, 33, 33)), padding=16) < 1).to(dtype=torch.float32))
+        voted = (torch.sum(torch.stack(keeps), dim=0) > NW - 1).to(dtype=torch.float32)       # :93
+        out = {"inv_depth": inv_depth.numpy(), "image": image.numpy(), "K": K.numpy(), "pose": pose.numpy(),
+               "cv_masks": torch.stack(cv_masks).numpy(), "keeps": torch.stack(keeps).numpy()}
+        for tag, roi, use_vote in (("plain", None, False), ("roi_vote", [4, 36, 6, 60], True)):
+            saver = PLYSaver(H, W, min_d=3, max_d=30, batch_size=B, roi=roi, dropout=0)
+            depth = inv_depth.clone()
+            if use_vote:
+                depth *= voted                                                               # :95
+            saver.add_depthmap(depth, image.clone(), K.clone(), pose.clone())
+            v = np.array(saver.data, dtype=np.float32).reshape(-1, 6)
+            out[f"vertices_{tag}"] = v
+            print(tag, v.shape, "kept share", v.shape[0] / (B * H * W))
+        np.savez_compressed(HERE / "pointcloud.npz", **out)
         return
     if "--only-d64f6" in sys.argv:
         # BASELINE config 5's plane and frame counts (64 planes, 6 source frames) at a small size; added after the other
