@@ -516,6 +516,126 @@ __device__ __forceinline__ void march_unit(const Stage1Ctx& c1, const Stage2Ctx&
     __syncwarp();
 }
 
+// ---- per-pixel phase: view weights (monorec_model.py:257-260), zeroing of invalid pixels (:251) and fusion
+//      cv = sum_f w_f (1 - 2 sad_f) / sum_f w_f, 0 where sum_f w_f == 0 (:262-269).  T lanes share a pixel, each with a chunk of
+//      kChunk planes in registers (T = 1 for D <= 32, 2 for D <= 64, 4 for D <= 128): every (L2-hot) single-frame value is
+//      read back exactly once; max / sum over the planes are combined across the T lanes by shuffles.
+struct PixelPhase {
+    float* cv;
+    float* sfcv;
+    void* sf_nhwc;
+    int sf_nhwc_half;
+    const unsigned char* vmask;
+    int B, F, D, H, W, TH, b, u0, v0;
+    float inv_dm1, kq;
+    uint64_t pol_stream;
+};
+
+template <int T>
+__device__ __forceinline__ void pixel_phase(const PixelPhase& c, const int tid) {
+    constexpr int kSlots = 32 / T;                       // pixels per warp iteration
+    const int lane = tid & 31, warp = tid >> 5;
+    const int sub = lane % kSlots, chunk = lane / kSlots;
+    const int D = c.D, F = c.F, TH = c.TH;
+    const int d_lo = chunk * kChunk;                     // this lane's planes [d_lo, d_lo + kChunk) of D
+    const size_t plane = (size_t)c.H * c.W;
+    const size_t pstride = plane * sizeof(float);        // bytes between the planes of a pixel
+    const size_t fstride = (size_t)c.B * D * pstride;    // bytes between the frames
+    const int vstride = TH * kTileCols;
+    const int per_iter = kWarps * kSlots;
+    for (int p0 = 0; p0 < TH * kTileCols; p0 += per_iter) {
+        const int p = p0 + warp * kSlots + sub;
+        const int r = p >> 6, bc = p & 63;
+        const int u = c.u0 + bc, v = c.v0 + r;
+        const bool own = (p < TH * kTileCols) && (bc >= 2) && (bc < 2 + kOutCols) && (u < c.W) && (v < c.H);
+        if (T == 1 && !own) continue;                    // (with T > 1 every lane stays for the shuffles)
+        const size_t pix = own ? (size_t)v * c.W + u : 0;
+        // addresses advance by pointer increments (one 64-bit add per access; an index expression costs a wide multiply each)
+        char* cv_out = reinterpret_cast<char*>(c.cv + ((size_t)c.b * D + d_lo) * plane + pix);
+        char* sf = reinterpret_cast<char*>(c.sfcv + ((size_t)c.b * D + d_lo) * plane + pix);       // frame f: + f * fstride
+        float acc[kChunk], vv[kChunk];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
+        float wsum = 0.f;
+        for (int f = 0; f < F; ++f, sf += fstride) {
+            const bool valid = own && (c.vmask[f * vstride + p] != 0);
+            char* nh = nullptr;                          // this pixel's D channels of frame f in the NHWC copy (T == 1 only)
+            if (T == 1 && c.sf_nhwc != nullptr)
+                nh = static_cast<char*>(c.sf_nhwc) + (((size_t)f * c.B + c.b) * plane + pix) * D * (c.sf_nhwc_half ? 2 : 4);
+            char* q = sf;
+            if (own && !valid) {                         // invalid pixel of frame f: the whole plane stack is 0
+#pragma unroll 4
+                for (int j = 0; j < kChunk; ++j, q += pstride)
+                    if (d_lo + j < D) *reinterpret_cast<float*>(q) = 0.f;
+                if (nh != nullptr)
+                    for (int o = 0; o < D * (c.sf_nhwc_half ? 2 : 4); o += 16) *reinterpret_cast<uint4*>(nh + o) = make_uint4(0, 0, 0, 0);
+            }
+            if (T == 1 && !valid) continue;
+            if (valid) {
+                if (D == T * kChunk) {                   // 32 / 64 / 128 planes: no per-plane predicates
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j, q += pstride) vv[j] = __ldcg(reinterpret_cast<const float*>(q));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kChunk; ++j, q += pstride) vv[j] = (d_lo + j < D) ? __ldcg(reinterpret_cast<const float*>(q)) : -2.0f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) vv[j] = -2.0f;
+            }
+            float m4[4] = {-2.0f, -2.0f, -2.0f, -2.0f};
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) m4[j & 3] = fmaxf(m4[j & 3], vv[j]);
+            float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+#pragma unroll
+            for (int s = kSlots; s < 32; s <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+            const float km = c.kq * m;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) {
+                const float t = fmaf(-c.kq, vv[j], km);
+                float e;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * t));
+                if (D == T * kChunk || d_lo + j < D) s4[j & 3] += e;
+            }
+            float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+#pragma unroll
+            for (int s = kSlots; s < 32; s <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+            // weight = 1 - 1/(D-1) * (sum - 1): separate roundings as in the reference so that flat-cost pixels
+            // (sum == D) give exactly 0 (monorec_model.py:258, :265-269)
+            const float w = valid ? __fsub_rn(1.0f, __fmul_rn(c.inv_dm1, __fsub_rn(sum, 1.0f))) : 0.f;
+            wsum += w;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j) acc[j] = fmaf(w, vv[j], acc[j]);
+            if (nh != nullptr) {                         // the MaskModule's input layout, written while the values are in registers
+                if (c.sf_nhwc_half) {
+#pragma unroll
+                    for (int j = 0; j < kChunk; j += 8) {
+                        if (j >= D) break;
+                        uint4 pk;
+                        __half2* h = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(vv[j + 2 * k], vv[j + 2 * k + 1]);
+                        *reinterpret_cast<uint4*>(nh + 2 * j) = pk;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kChunk; j += 4) {
+                        if (j >= D) break;
+                        *reinterpret_cast<float4*>(nh + 4 * j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
+                    }
+                }
+            }
+        }
+        if (!own) continue;
+        const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
+        char* q = cv_out;
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j, q += pstride)
+            if (D == T * kChunk || d_lo + j < D) st_hint_f1(reinterpret_cast<float*>(q), acc[j] * inv, c.pol_stream);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, MR_CV_MINBLOCKS)
 cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -821,142 +941,17 @@ cost_volume_kernel(const CvArgs a, const __grid_constant__ CvMaps maps) {
     // ---- per-pixel phase: view weights (monorec_model.py:257-260), zeroing of invalid pixels (:251) and fusion
     //      cv = sum_f w_f (1 - 2 sad_f) / sum_f w_f, 0 where sum_f w_f == 0 (:262-269).  Each thread reads back the
     //      L2-hot single-frame values of its pixel once per frame. ------------------------------------------------------
+    PixelPhase pp;
+    pp.cv = a.cv; pp.sfcv = a.sfcv; pp.sf_nhwc = a.sf_nhwc; pp.sf_nhwc_half = a.sf_nhwc_half;
+    pp.vmask = vmask; pp.B = a.B; pp.F = F; pp.D = D; pp.H = H; pp.W = W; pp.TH = TH; pp.b = b; pp.u0 = u0; pp.v0 = v0;
+    pp.inv_dm1 = a.inv_dm1;
     // exp(-alpha (sad - min sad)^2) with sad = (1 - sv) / 2 is ex2(-(k (max sv - sv))^2), k = sqrt(alpha log2(e)) / 2
-    const float kq = 0.5f * sqrtf(a.alpha * 1.4426950408889634f);
-    const size_t pstride = plane * sizeof(float);                    // bytes between the planes of a pixel
-    const size_t fstride = (size_t)a.B * D * pstride;                // bytes between the frames
-    float* wsm = reinterpret_cast<float*>(smem + L.ytile);           // D > kChunk: [F][kThreads] view weights (the tables are idle)
-    for (int p = tid; p < TH * kTileCols && MR_CV_SKIP != 2; p += kThreads) {
-        const int r = p >> 6, bc = p & 63;
-        const int u = u0 + bc, v = v0 + r;
-        const bool own = (bc >= 2) && (bc < 2 + kOutCols) && (u < W) && (v < H);
-        if (!own) continue;
-        const size_t pix = (size_t)v * W + u;
-        char* cv_out = reinterpret_cast<char*>(a.cv + (size_t)b * D * plane + pix);
-        char* sf0 = reinterpret_cast<char*>(a.sfcv + ((size_t)b * D) * plane + pix);       // frame f: + f * fstride
-        const unsigned char* vm = vmask + p;
-        const int vstride = TH * kTileCols;
-        // addresses advance by pointer increments (one 64-bit add per access; an index expression costs a wide multiply each)
-        auto view_weight = [&](const float (&vv)[kChunk], const int n) {
-            float m4[4] = {-2.0f, -2.0f, -2.0f, -2.0f};
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) m4[j & 3] = fmaxf(m4[j & 3], (j < n) ? vv[j] : -2.0f);
-            const float km = kq * fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-                const float t = fmaf(-kq, vv[j], km);
-                float e;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * t));
-                if (j < n) s4[j & 3] += e;
-            }
-            return (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        };
-        if (D <= kChunk) {
-            float acc[kChunk], vv[kChunk];
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
-            float wsum = 0.f;
-            char* sf = sf0;
-            for (int f = 0; f < F; ++f, sf += fstride) {
-                char* q = sf;
-                char* nh = nullptr;           // this pixel's D channels of frame f in the NHWC copy
-                if (a.sf_nhwc != nullptr)
-                    nh = static_cast<char*>(a.sf_nhwc) + (((size_t)f * a.B + b) * plane + pix) * D * (a.sf_nhwc_half ? 2 : 4);
-                if (vm[f * vstride] == 0) {   // invalid pixel of frame f: the whole plane stack is 0
-                    for (int d = 0; d < D; ++d, q += pstride) *reinterpret_cast<float*>(q) = 0.f;
-                    if (nh != nullptr)
-                        for (int o = 0; o < D * (a.sf_nhwc_half ? 2 : 4); o += 16) *reinterpret_cast<uint4*>(nh + o) = make_uint4(0, 0, 0, 0);
-                    continue;
-                }
-                float sum;
-                if (D == kChunk) {            // every shipped configuration: no per-plane predicates
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j, q += pstride) vv[j] = __ldcg(reinterpret_cast<const float*>(q));
-                    sum = view_weight(vv, kChunk);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j, q += pstride) vv[j] = (j < D) ? __ldcg(reinterpret_cast<const float*>(q)) : -2.0f;
-                    sum = view_weight(vv, D);
-                }
-                // weight = 1 - 1/(D-1) * (sum - 1): separate roundings as in the reference so that flat-cost pixels
-                // (sum == D) give exactly 0 (monorec_model.py:258, :265-269)
-                const float w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
-                wsum += w;
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) acc[j] = fmaf(w, vv[j], acc[j]);
-                if (nh != nullptr) {          // the MaskModule's input layout, written while the values are in registers
-                    if (a.sf_nhwc_half) {
-#pragma unroll
-                        for (int j = 0; j < kChunk; j += 8) {
-                            if (j >= D) break;
-                            uint4 pk;
-                            __half2* h = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(vv[j + 2 * k], vv[j + 2 * k + 1]);
-                            *reinterpret_cast<uint4*>(nh + 2 * j) = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < kChunk; j += 4) {
-                            if (j >= D) break;
-                            *reinterpret_cast<float4*>(nh + 4 * j) = make_float4(vv[j], vv[j + 1], vv[j + 2], vv[j + 3]);
-                        }
-                    }
-                }
-            }
-            const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
-            char* q = cv_out;
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j, q += pstride)
-                if (j < D) st_hint_f1(reinterpret_cast<float*>(q), acc[j] * inv, pol_stream);
-            continue;
-        }
-        // D > kChunk: view weights first (two passes over the L2-hot planes of each frame), then the fused volume in chunks
-        float wsum = 0.f;
-        {
-            char* sf = sf0;
-            for (int f = 0; f < F; ++f, sf += fstride) {
-                float w = 0.f;
-                char* q = sf;
-                if (vm[f * vstride] == 0) {
-                    for (int d = 0; d < D; ++d, q += pstride) *reinterpret_cast<float*>(q) = 0.f;
-                } else {
-                    float m = -2.0f, sum = 0.f;
-                    for (int d = 0; d < D; ++d, q += pstride) m = fmaxf(m, __ldcg(reinterpret_cast<const float*>(q)));
-                    const float km = kq * m;
-                    q = sf;
-                    for (int d = 0; d < D; ++d, q += pstride) {
-                        const float t = fmaf(-kq, __ldcg(reinterpret_cast<const float*>(q)), km);
-                        float e;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-t * t));
-                        sum += e;
-                    }
-                    w = __fsub_rn(1.0f, __fmul_rn(a.inv_dm1, __fsub_rn(sum, 1.0f)));
-                }
-                wsm[f * kThreads + tid] = w;
-                wsum += w;
-            }
-        }
-        const float inv = (wsum == 0.f) ? 0.f : 1.0f / wsum;
-        for (int d0 = 0; d0 < D; d0 += kChunk) {
-            float acc[kChunk];
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j) acc[j] = 0.f;
-            char* sf = sf0 + (size_t)d0 * pstride;
-            for (int f = 0; f < F; ++f, sf += fstride) {
-                const float w = wsm[f * kThreads + tid];
-                if (w == 0.f) continue;   // invalid (or weightless) frames add nothing
-                char* q = sf;
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j, q += pstride)
-                    if (d0 + j < D) acc[j] = fmaf(w, __ldcg(reinterpret_cast<const float*>(q)), acc[j]);
-            }
-            char* q = cv_out + (size_t)d0 * pstride;
-#pragma unroll
-            for (int j = 0; j < kChunk; ++j, q += pstride)
-                if (d0 + j < D) st_hint_f1(reinterpret_cast<float*>(q), acc[j] * inv, pol_stream);
-        }
+    pp.kq = 0.5f * sqrtf(a.alpha * 1.4426950408889634f);
+    pp.pol_stream = pol_stream;
+    if (MR_CV_SKIP != 2) {
+        if (D <= kChunk) pixel_phase<1>(pp, tid);
+        else if (D <= 2 * kChunk) pixel_phase<2>(pp, tid);
+        else pixel_phase<4>(pp, tid);
     }
 }
 
