@@ -22,6 +22,7 @@ __all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "Res
 # in half mode the cuDNN trunk runs in half as well (folded weights and activations): its NHWC outputs feed the conv engine
 # without casts (0.82 -> 0.71 ms at B=8); MONOREC_B200_TRUNK=cudnn_f32 keeps it in fp32
 TRUNK_CUDNN_F16 = os.environ.get("MONOREC_B200_TRUNK", "cudnn_f16").lower() != "cudnn_f32"
+TRUNK_FUSED = os.environ.get("MONOREC_B200_TRUNK_FUSED", "1") != "0"
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -159,14 +160,27 @@ class ResnetEncoder(nn.Module):
                 self._fold_half_sig = self._fold_sig
             f = self._fold_half
             x = x.half()
-        x = F.conv2d(x, *f["stem"], stride=e.conv1.stride, padding=e.conv1.padding).relu_()
+        # cuDNN's fused epilogues where the build offers them (conv + bias + ReLU, conv + residual + bias + ReLU: the ~24
+        # element-wise add / clamp launches of the trunk disappear); MONOREC_B200_TRUNK_FUSED=0 keeps separate ATen ops
+        fused = TRUNK_FUSED and x.is_cuda and hasattr(torch, "cudnn_convolution_relu") and hasattr(torch, "cudnn_convolution_add_relu")
+
+        def conv_relu(t, w, bias, stride, padding):
+            if fused:
+                return torch.cudnn_convolution_relu(t, w, bias, list(stride), list(padding), [1, 1], 1)
+            return F.conv2d(t, w, bias, stride=stride, padding=padding).relu_()
+
+        def conv_add_relu(t, w, bias, z):
+            if fused:
+                return torch.cudnn_convolution_add_relu(t, w, z, 1.0, bias, [1, 1], [1, 1], [1, 1], 1)
+            return F.conv2d(t, w, bias, padding=1).add_(z).relu_()
+        x = conv_relu(x, f["stem"][0], f["stem"][1], tuple(e.conv1.stride), tuple(e.conv1.padding))
         self.features = [x]
         x = e.maxpool(x)
         for blocks in f["blocks"]:
             for (w1, b1), stride, (w2, b2), down in blocks:
                 idt = x if down is None else F.conv2d(x, down[0], down[1], stride=down[2])
-                out = F.conv2d(x, w1, b1, stride=stride, padding=1).relu_()
-                x = F.conv2d(out, w2, b2, padding=1).add_(idt).relu_()
+                out = conv_relu(x, w1, b1, tuple(stride), (1, 1))
+                x = conv_add_relu(out, w2, b2, idt)
             self.features.append(x)
         return self.features
 
