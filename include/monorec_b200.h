@@ -244,6 +244,24 @@ int mr_pointcloud_add(const float* inv_depth, const float* keyframe, const float
                       float* vertices, long long capacity, long long n_before, long long* n_after,
                       void* workspace, long long workspace_bytes, void* stream);
 
+/* ---- photometric reprojection loss, forward and backward -------------------------------------------
+ * Replaces reprojection_loss (reference: model/loss_functions/common_losses.py:16-114) with error_function=compute_errors
+ * (:10-13), combine_frames="min", mono_auto=False, reduce=False -- the argument sets of model/loss_functions/monorec_loss.py
+ * :185-188, :264-265, :355, :361 -- and torch autograd of it w.r.t. the predicted inverse depth (trainer/monorec_trainer.py
+ * :143-145).  proj: [B,F,12] rows of mr_projection_tables (depths = NULL) for the F source frames of this call (mono frames
+ * and / or the stereo frame); inv_depth: [B,1,H,W] `depth_prediction`.
+ *   mr_reprojection_loss_fwd: out_errors [B,H,W] = min over the frames of 0.85 mean_c SSIM + 0.15 mean_c |warped - keyframe|
+ *     (Gaussian 3x3 window, zero padding, comp mode: model/layers.py:79-139), +inf where no frame gives a usable sample
+ *     (:57 / border > 0: :60-61; automasking != 0: :80-83); out_winner [B,H,W] = index of the frame giving the minimum, -1: none.
+ *   mr_reprojection_loss_bwd: out_grad_inv_depth [B,1,H,W] = d (sum_p grad_errors[p] errors[p]) / d inv_depth; grad_errors at
+ *     pixels whose winner is -1 is ignored.  Needs nothing from the forward pass but out_winner. */
+int mr_reprojection_loss_fwd(const float* keyframe, const float* const* frames, const float* proj, const float* inv_depth,
+                             int B, int F, int H, int W, int automasking, int border, float* out_errors, int* out_winner,
+                             void* stream);
+int mr_reprojection_loss_bwd(const float* keyframe, const float* const* frames, const float* proj, const float* inv_depth,
+                             const float* grad_errors, const int* winner, int B, int F, int H, int W,
+                             float* out_grad_inv_depth, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

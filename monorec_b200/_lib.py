@@ -55,6 +55,10 @@ SIGNATURES = {
     "mr_pointcloud_add": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int,
                                   c_float, c_float, POINTER(c_int), c_void_p, c_float, c_void_p, c_longlong, c_longlong, c_void_p,
                                   c_void_p, c_longlong, c_void_p]),
+    "mr_reprojection_loss_fwd": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p, c_void_p]),
+    "mr_reprojection_loss_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_void_p]),
     "mr_mask_volume": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 

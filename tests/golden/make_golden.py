@@ -22,6 +22,8 @@ Files written
                           cv_mask, 4 depth maps, image_features checksums
   pointcloud.npz          the reference's PLYSaver.add_depthmap + mask dilation / vote on seeded inputs (`--only-pointcloud`)
   metrics.npz             the reference's seven sparse depth metrics on seeded inputs, four parameter sets (`--only-metrics`)
+  reprojection.npz        the reference's reprojection_loss (model/loss_functions/common_losses.py) and its autograd gradient
+                          w.r.t. the predicted inverse depth on seeded inputs, three argument sets (`--only-reprojection`)
   model_fp64.npz          the same two model configurations evaluated by the reference in float64 (`--only-model-fp64`):
                           the reference's own fp32 rounding noise on `result` / `cv_mask`, which sizes the GPU gates
 """
@@ -39,6 +41,7 @@ REF = Path(os.environ.get("MONOREC_REFERENCE", "/root/reference"))
 sys.path.insert(0, str(REPO))
 
 from monorec_b200.synthetic import make_inputs, seeded_state_dict  # noqa: E402
+
 
 
 def import_reference():
@@ -275,6 +278,33 @@ def main():
             out[f"vertices_{tag}"] = v
             print(tag, v.shape, "kept share", v.shape[0] / (B * H * W))
         np.savez_compressed(HERE / "pointcloud.npz", **out)
+        return
+    if "--only-reprojection" in sys.argv:
+        # the unmodified reprojection_loss (model/loss_functions/common_losses.py:16-114) with the argument sets the reference's
+        # losses use (monorec_loss.py:185-188, :355, :361), reduce=False, and torch autograd of sum(weights * errors) w.r.t.
+        # the predicted inverse depth
+        sys.path.insert(0, str(REF))
+        from model.loss_functions.common_losses import reprojection_loss, compute_errors  # noqa
+        from tests.helpers import REPROJ_CFG, reprojection_inputs  # noqa
+        d, invd, wts = reprojection_inputs()
+        out = {"cfg": np.array(REPROJ_CFG), "invd": invd.numpy(), "weights": wts.numpy()}
+        cases = {"plain": dict(use_mono=True, use_stereo=False, automasking=False),
+                 "auto": dict(use_mono=True, use_stereo=True, automasking=True),
+                 "stereo_border": dict(use_mono=False, use_stereo=True, automasking=False, border=3)}
+        for tag, kw in cases.items():
+            pred = invd.clone().requires_grad_(True)
+            err = reprojection_loss(pred, {k: (list(v) if isinstance(v, list) else v) for k, v in d.items()},
+                                    error_function=compute_errors, reduce=False, combine_frames="min", mono_auto=False, **kw)
+            inf = torch.isinf(err)
+            (torch.where(inf, torch.zeros_like(err), err) * wts).sum().backward()
+            red = reprojection_loss(invd.clone(), {k: (list(v) if isinstance(v, list) else v) for k, v in d.items()},
+                                    error_function=compute_errors, reduce=True, combine_frames="min", mono_auto=False, **kw)
+            out[f"errors_{tag}"] = err.detach().numpy()
+            out[f"grad_{tag}"] = pred.grad.numpy()
+            out[f"reduced_{tag}"] = np.array(float(red))
+            print(tag, "inf share", float(inf.float().mean()), "mean finite error", float(err[~inf].mean()),
+                  "max |grad|", float(pred.grad.abs().max()), "reduced", float(red))
+        np.savez_compressed(HERE / "reprojection.npz", **out)
         return
     if "--only-d64f6" in sys.argv:
         # BASELINE config 5's plane and frame counts (64 planes, 6 source frames) at a small size; added after the other

@@ -74,3 +74,26 @@ def compare_volumes(cv, sf, ref_cv, ref_sf, tol=1e-3, max_flip_px_per_frame=4):
     stats["argmax_agree_gated"], stats["argmax_agree_raw"] = agree_gated, agree_raw
     assert agree_gated == 1.0, f"argmax differs on pixels with margin > 1e-4: agreement {agree_gated}"
     return stats
+
+REPROJ_CFG = (2, 2, 48, 80, 31)    # B, F, H, W, seed of tests/golden/reprojection.npz
+
+
+def reprojection_inputs():
+    """Seeded inputs of the reprojection-loss golden: the synthetic dict plus a stereo frame (0.54 m baseline), a smooth
+    predicted inverse depth in [0.02, 0.3] with pixel noise, and positive weights for the scalar that is differentiated.
+    Shared by tests/golden/make_golden.py --only-reprojection and tests/test_reprojection.py (the inputs are re-created, not stored)."""
+    B, Fn, H, W, seed = REPROJ_CFG
+    from monorec_b200.synthetic import make_inputs
+    d = make_inputs(B, Fn, H, W, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    d["stereoframe"] = torch.round((torch.roll(d["keyframe"], shifts=(1, 4), dims=(2, 3)) + 0.5) * 255.0) / 255.0 - 0.5
+    pose = torch.eye(4).unsqueeze(0).repeat(B, 1, 1)
+    pose[:, 0, 3] = 0.54
+    d["stereoframe_pose"] = pose
+    d["stereoframe_intrinsics"] = d["keyframe_intrinsics"].clone()
+    yy = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1) / H
+    xx = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W) / W
+    invd = 0.16 + 0.13 * torch.sin(5.0 * xx + 2.0 * yy + torch.rand(B, 1, 1, 1, generator=g) * 6.28)
+    invd = (invd + 0.01 * (torch.rand(B, 1, H, W, generator=g) - 0.5)).clamp(0.02, 0.3).contiguous()
+    wts = (torch.rand(B, H, W, generator=g) + 0.5).contiguous()
+    return d, invd, wts
