@@ -49,6 +49,8 @@ struct TcArgs {
     uint32_t idesc;                // UMMA instruction descriptor
     int row_bytes;                 // bytes of one K chunk row in shared memory = swizzle span: 128, or 64 (half sources, 32-channel chunks)
     uint64_t desc_hi;              // smem descriptor without the start address (LBO, SBO = 8 rows, version, swizzle mode)
+    int halo_pitch;                // halo kernel: pixels per input row of the shared-memory box (8 outputs + kw - 1 taps to the right)
+    uint32_t halo_a_bytes;         // halo kernel: bytes of one input stage (box rounded up to 1 KB)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
@@ -433,21 +435,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // -------------------------------------------------------------------------------------------------------------------------
 // Stride-1 layers with small weights (the full-resolution 24..64-channel layers that dominate the stacks): "halo" variant.
 //   * the whole packed weight tensor of the layer is loaded into shared memory ONCE per CTA (resident B);
-//   * per (tile, source, 32-channel chunk) ONE TMA box {32 ch, 16 px, 16 + kh - 1 px} brings the input tile with its halo;
+//   * per (tile, source, K chunk) ONE TMA box {chunk, P px, 16 + kh - 1 px}, P = 8 + kw - 1, brings the input tile with its halo
+//     (exactly the pixels the taps touch: a (k x 1) layer loads 8-px rows, a 3 x 3 layer 10-px rows);
 //     every filter tap is then just a different shared-memory descriptor into that box: start address shifted by
-//     (ky * 16 + kx) rows of 128 B, stride between 8-row groups = one halo row (2048 B), swizzle phase carried by the
-//     descriptor's base-offset field.  L2->SM traffic drops from kh*kw boxes per tile to one.
+//     (ky * P + kx) rows of 128 / 64 B, stride between 8-row groups = one halo row (P rows); the swizzle is a function of the
+//     absolute shared-memory address, so neither shift needs to be a multiple of the 8-row swizzle atom.
+//     L2->SM traffic drops from kh*kw boxes per tile to one.
 // Output tile = 16 rows x 8 columns (an 8-row MMA group = 8 adjacent pixels of one output row).
 // -------------------------------------------------------------------------------------------------------------------------
 #ifndef MR_HALO_BASE_OFFSET
 #define MR_HALO_BASE_OFFSET 0
 #endif
-constexpr int kHaloPitch = 16;   // pixels per halo row in smem (8 outputs + up to 8 taps to the right)
-
-__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_bytes) {
-    // K-major swizzled (128- or 64-byte rows), SBO = one halo row (16 px), base offset 0: the swizzle is a function of the
+__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_bytes, uint32_t pitch) {
+    // K-major swizzled (128- or 64-byte rows), SBO = one halo row (`pitch` px), base offset 0: the swizzle is a function of the
     // absolute shared-memory address; MR_HALO_BASE_OFFSET=1 restores the row-phase variant for experiments
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((kHaloPitch * row_bytes) >> 4) << 32) |
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((pitch * row_bytes) >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)(MR_HALO_BASE_OFFSET ? ((saddr >> 7) & 7) : 0) << 49) |
            ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
 }
@@ -470,7 +472,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
     const int taps = a.kh * a.kw;
     const uint32_t bres_bytes = (uint32_t)(taps * chunks_per_tap) * b_bytes;       // multiple of 1024 (n_pad % 16 == 0)
-    const uint32_t a_bytes = (uint32_t)(16 + a.kh - 1) * kHaloPitch * row_bytes;   // multiple of 1024 (pitch 16)
+    const uint32_t a_bytes = a.halo_a_bytes;                                       // multiple of 1024
+    const uint32_t pitch = (uint32_t)a.halo_pitch;
+    const uint32_t a_tx = (uint32_t)(16 + a.kh - 1) * pitch * row_bytes;           // bytes one box delivers
     const uint32_t a_base = base + ((bres_bytes + 1023u) & ~1023u);
     const int stages = a.stages;
     const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[4]);
@@ -518,7 +522,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         const int st = it % stages;
                         const uint32_t ph = (uint32_t)(it / stages) & 1u;
                         mbar_wait(aempty0 + 8 * st, ph ^ 1u);
-                        mbar_expect_tx(afull0 + 8 * st, a_bytes);
+                        mbar_expect_tx(afull0 + 8 * st, a_tx);
                         tma_load_4d(a_base + st * a_bytes, tm, afull0 + 8 * st, j * a.kc, ix0, iy0, b);
                     }
                 }
@@ -543,7 +547,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const uint32_t sa = a_base + st * a_bytes;
                     for (int ky = 0; ky < a.kh; ++ky)
                         for (int kx = 0; kx < a.kw; ++kx) {
-                            const uint64_t da = make_desc_halo(sa + (uint32_t)(ky * kHaloPitch + kx) * row_bytes, row_bytes);
+                            const uint64_t da = make_desc_halo(sa + ((uint32_t)ky * pitch + (uint32_t)kx) * row_bytes, row_bytes, pitch);
                             const uint32_t sb = base + (uint32_t)((ky * a.kw + kx) * chunks_per_tap + cg) * b_bytes;
                             const uint64_t db = (uint64_t)((sb & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) |
                                                 ((uint64_t)1 << 46) | ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
@@ -663,7 +667,10 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, i
     static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : true;
     // (64-byte rows are fine inside the halo box too: half sources of <= 32 channels packed with 32-channel chunks; measured
     // 429 -> 203 us on the 32->32 3x3 layer over the single-frame volumes, profiles/r02_k2_variants.txt)
-    const size_t halo_a_bytes = (size_t)(16 + d.kh - 1) * kHaloPitch * a.row_bytes;
+    // MONOREC_B200_TC_HALO_PITCH=16: the fixed 16-px rows of the first halo kernel (A/B measurements)
+    static const int pitch_env = getenv("MONOREC_B200_TC_HALO_PITCH") ? atoi(getenv("MONOREC_B200_TC_HALO_PITCH")) : 0;
+    const int halo_pitch = (pitch_env >= 8 + d.kw - 1) ? pitch_env : 8 + d.kw - 1;
+    const size_t halo_a_bytes = ((size_t)(16 + d.kh - 1) * halo_pitch * a.row_bytes + 1023) & ~size_t(1023);
     const size_t bres_al = (bres + 1023) & ~size_t(1023);
     auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights (228 KB per SM, 1 KB reserved + ~1.1 KB static per CTA)
         const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas - 8 * 1024;   // 8 KB: the epilogue's staging buffers (static)
@@ -689,7 +696,7 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, i
         const cuuint64_t gstr[3] = {(cuuint64_t)C * esize, (cuuint64_t)d.Ws * C * esize, (cuuint64_t)d.Hs * d.Ws * C * esize};
         // with a traversal stride s the box spans box/s loaded elements: 16 (8) output pixels need a span of 16*s (8*s)
         cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(kTileW * d.sx), (cuuint32_t)(kTileH * d.sy), 1};
-        if (halo) { box[1] = kHaloPitch; box[2] = (cuuint32_t)(16 + d.kh - 1); }
+        if (halo) { box[1] = (cuuint32_t)halo_pitch; box[2] = (cuuint32_t)(16 + d.kh - 1); }
         const cuuint32_t estr[4] = {1, (cuuint32_t)d.sx, (cuuint32_t)d.sy, 1};
         CUresult r = encode(&tmA[s], f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d.src[s]), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -750,6 +757,8 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, i
     a.act = d.act; a.act_a = d.act_a; a.act_b = d.act_b; a.round_out = round_out;
     if (halo) {
         a.stages = halo_stages;
+        a.halo_pitch = halo_pitch;
+        a.halo_a_bytes = (uint32_t)halo_a_bytes;
         const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
         int grid = sms * halo_ctas;
         if (grid > a.total_tiles) grid = a.total_tiles;

@@ -177,7 +177,8 @@ def fp32_mode():
 @pytest.mark.parametrize("cin,cout,kh,kw,sy,sx,H,W", [
     (32, 32, 3, 3, 1, 1, 16, 32), (36, 48, 7, 1, 1, 1, 24, 40), (48, 64, 7, 1, 2, 1, 24, 40), (64, 64, 1, 7, 1, 2, 12, 40),
     (64, 128, 5, 1, 2, 1, 20, 24), (128, 128, 1, 5, 1, 2, 10, 24), (192, 256, 3, 1, 2, 1, 18, 16), (32, 24, 3, 3, 1, 1, 9, 21),
-    (96, 96, 3, 3, 1, 1, 7, 13), (256, 256, 1, 3, 1, 1, 16, 32), (48, 48, 3, 3, 1, 1, 64, 128)])
+    (96, 96, 3, 3, 1, 1, 7, 13), (256, 256, 1, 3, 1, 1, 16, 32), (48, 48, 3, 3, 1, 1, 64, 128),
+    (48, 48, 1, 7, 1, 1, 24, 40), (96, 32, 3, 1, 1, 1, 24, 40), (32, 32, 1, 3, 1, 1, 24, 40), (24, 32, 2, 2, 1, 1, 20, 28)])   # halo rows of 14 / 8 / 10 / 9 px
 def test_tc_conv_matches_torch(tf32_mode, cin, cout, kh, kw, sy, sx, H, W):
     from monorec_b200 import conv as C
     from oracle.convnet_oracle import conv_same
@@ -313,7 +314,8 @@ def f16_mode():
 
 @pytest.mark.parametrize("cin,cout,kh,kw,sy,sx,H,W", [
     (32, 32, 3, 3, 1, 1, 16, 32), (40, 48, 7, 1, 1, 1, 24, 40), (48, 64, 7, 1, 2, 1, 24, 40), (64, 64, 1, 7, 1, 2, 12, 40),
-    (128, 128, 1, 5, 1, 2, 10, 24), (192, 256, 3, 1, 2, 1, 18, 16), (32, 24, 3, 3, 1, 1, 9, 21), (96, 96, 3, 3, 1, 1, 7, 13)])
+    (128, 128, 1, 5, 1, 2, 10, 24), (192, 256, 3, 1, 2, 1, 18, 16), (32, 24, 3, 3, 1, 1, 9, 21), (96, 96, 3, 3, 1, 1, 7, 13),
+    (48, 48, 3, 3, 1, 1, 64, 128), (48, 48, 1, 7, 1, 1, 24, 40), (96, 32, 3, 1, 1, 1, 24, 40), (32, 32, 1, 3, 1, 1, 24, 40)])
 def test_f16_conv_matches_torch(f16_mode, cin, cout, kh, kw, sy, sx, H, W):
     from monorec_b200 import conv as C
     from oracle.convnet_oracle import conv_same

@@ -32,6 +32,12 @@ def timed(fn, n=10):
 cases = [("mask enc0 3x3 32->32 B32 full", 32, 256, 512, (32,), 32, 3, 3),
          ("depth enc0 7x1 40->48 B8 full", 8, 256, 512, (40,), 48, 7, 1),
          ("depth enc0 1x7 48->48 B8 full", 8, 256, 512, (48,), 48, 1, 7),
+         ("depth enc0 3x1 48->48 B8 full", 8, 256, 512, (48,), 48, 3, 1),
+         ("depth enc0 1x3 48->48 B8 full", 8, 256, 512, (48,), 48, 1, 3),
+         ("depth dec4 3x1 48+48->32 B8 full", 8, 256, 512, (48, 48), 32, 3, 1),
+         ("depth dec4 1x3 32->32 B8 full", 8, 256, 512, (32,), 32, 1, 3),
+         ("depth dec4 3x3 32->24 B8 full", 8, 256, 512, (32,), 24, 3, 3),
+         ("depth enc1 3x1 64->64 B8 half", 8, 128, 256, (64,), 64, 3, 1),
          ("mask dec3.2 3x3 48->48 B8 full", 8, 256, 512, (48,), 48, 3, 3),
          ("mask dec3.1 3x3 32+64->48 B8 full", 8, 256, 512, (32, 64), 48, 3, 3),
          ("mask enc1 3x3 48->48 B32 half", 32, 128, 256, (48,), 48, 3, 3),
