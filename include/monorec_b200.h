@@ -163,6 +163,12 @@ int mr_conv2d_nhwc(const mr_conv_desc* desc, void* stream);
  * results).  Tuning switches (environment, read once): MONOREC_B200_TC_HALO=0|1|2, MONOREC_B200_TC_HALO_F16=0|1,
  * MONOREC_B200_TC_CTAS=n. */
 int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream);
+/* The sub-pixel convolutions of one layer -- Refine's ConvTranspose2d(k4,s2)+crop = four 2x2 filters (model/layers.py:380-400),
+ * Upconv's nearest-x2 + pad + 2x2 conv = 1x1 / 1x2 / 2x1 / 2x2 filters (:338-356) -- in ONE launch: descs[0..n_phases) share the
+ * sources, the destination, Cout, bias, activation and strides and differ in kh, kw, pad_t, pad_l, weight, oy_off, ox_off
+ * (anything else: MR_EINVAL).  Tiles are ordered (spatial tile, phase), so the phases of a tile run side by side and the input is
+ * read from HBM once instead of once per phase.  n_phases = 1 is mr_conv2d_nhwc_tc. */
+int mr_conv2d_nhwc_tc_phases(const mr_conv_desc* descs, int n_phases, int n_pad, int k_pad, int round_out, void* stream);
 /* Host-side weight packing for mr_conv2d_nhwc_tc (pure host code, callable without a GPU).
  *   mr_pack_conv_weights_bytes: size of the packed tensor and its n_pad / k_pad for a correlation kernel (Cout, sum src_c, kh, kw)
  *     whose input channels are the concatenation of n_src sources; dtype MR_DT_F32 (TF32-rounded fp32) or MR_DT_F16.

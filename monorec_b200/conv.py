@@ -329,6 +329,17 @@ def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f3
                           dtype=torch.float16 if (half and not out_f32) else torch.float32)
     wtc, n_pad, k_pad = L.wtc(half)
     d = ConvDesc()
+    _fill_desc(d, srcs, L, out, (Ho, Wo), pad, wtc, half, out_coff)
+    with torch.cuda.device(x0.device):
+        _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
+    return out
+
+
+def _fill_desc(d, srcs, L, out, out_hw, pad, wtc, half, out_coff=0):
+    x0 = srcs[0]
+    B, Hs, Ws, _ = x0.shape
+    sy, sx = L.stride
+    Ho, Wo = out_hw
     d.n_src = len(srcs)
     for i, s in enumerate(srcs):
         assert s.is_cuda and s.dtype == (torch.float16 if half else torch.float32) and s.is_contiguous()
@@ -345,9 +356,31 @@ def conv2d_tc(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f3
     d.oy_step, d.ox_step, d.oy_off, d.ox_off = L.out_step[0], L.out_step[1], L.out_off[0], L.out_off[1]
     d.act, d.act_a, d.act_b = L.act, L.act_a, L.act_b
     d.src_dtype, d.dst_dtype = (DT_F16 if half else DT_F32), _dt(out)
+
+
+def conv2d_tc_phases(srcs, subs, out, out_hw, round_out=True, half=False):
+    """The sub-pixel convolutions of one Refine / Upconv layer in ONE launch (mr_conv2d_nhwc_tc_phases): same sources and
+    destination, per-phase filter / padding / output offset; the phases of a spatial tile run side by side, so the input is
+    read from HBM once instead of once per phase."""
+    lib = _lib.load()
+    x0 = srcs[0]
+    descs = (ConvDesc * len(subs))()
+    n_pad = k_pad = None
+    keep = []
+    for d, L in zip(descs, subs):
+        wtc, n_pad_i, k_pad_i = L.wtc(half)
+        assert n_pad in (None, n_pad_i) and k_pad in (None, k_pad_i)
+        n_pad, k_pad = n_pad_i, k_pad_i
+        keep.append(wtc)
+        _fill_desc(d, srcs, L, out, out_hw, L.pad, wtc, half)
+        d.bias = subs[0].bias.data_ptr() if subs[0].bias is not None else None     # (one bias vector for all phases)
     with torch.cuda.device(x0.device):
-        _lib.check(lib.mr_conv2d_nhwc_tc(ctypes.byref(d), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc")
+        _lib.check(lib.mr_conv2d_nhwc_tc_phases(descs, len(subs), n_pad, k_pad, int(round_out), _stream(x0)), "mr_conv2d_nhwc_tc_phases")
     return out
+
+
+# MONOREC_B200_SUBPIXEL_ONE_LAUNCH=0: one launch per sub-pixel phase (A/B measurements)
+SUBPIXEL_ONE_LAUNCH = os.environ.get("MONOREC_B200_SUBPIXEL_ONE_LAUNCH", "1") != "0"
 
 
 class PackedSubpixel:
@@ -361,6 +394,12 @@ class PackedSubpixel:
         x0 = srcs[0]
         B, Hs, Ws, _ = x0.shape
         out = torch.empty(B, 2 * Hs, 2 * Ws, self.subs[0].cout, device=x0.device, dtype=x0.dtype)
+        L0 = self.subs[0]
+        half = MODE == "f16" and x0.dtype == torch.float16 and L0.tc_ok_f16
+        if SUBPIXEL_ONE_LAUNCH and (half or (MODE == "tf32" and L0.tc_ok)) and all(L.pad is not None for L in self.subs):
+            if FLOPS is not None:
+                FLOPS[0] += sum(2 * B * Hs * Ws * L.cout * sum(L.src_c) * L.kh * L.kw for L in self.subs)
+            return conv2d_tc_phases(srcs, self.subs, out, (Hs, Ws), round_out=not half, half=half)
         for L in self.subs:
             L(srcs, out=out, out_hw=(Hs, Ws))
         return out

@@ -49,6 +49,10 @@ struct TcArgs {
     uint32_t idesc;                // UMMA instruction descriptor
     int row_bytes;                 // bytes of one K chunk row in shared memory = swizzle span: 128, or 64 (half sources, 32-channel chunks)
     uint64_t desc_hi;              // smem descriptor without the start address (LBO, SBO = 8 rows, version, swizzle mode)
+    // tap-refetch kernel: up to 4 "phases" (the sub-pixel convolutions of one Refine / Upconv layer) share one launch; tile
+    // index = spatial tile * n_phase + phase, so the phases of a spatial tile run side by side and its input boxes are L2 hits
+    int n_phase;
+    int ph_kh[4], ph_kw[4], ph_pad_t[4], ph_pad_l[4], ph_oy_off[4], ph_ox_off[4];
     int halo_pitch;                // halo kernel: pixels per input row of the shared-memory box (8 outputs + kw - 1 taps to the right)
     uint32_t halo_a_bytes;         // halo kernel: bytes of one input stage (box rounded up to 1 KB)
 };
@@ -268,7 +272,7 @@ __device__ __forceinline__ void epilogue_staged(uint32_t trow, const TcArgs& a, 
 // path cannot take (unaligned channel slices, the rare activations) go through the generic out-of-line epilogue.
 template <int kTW, int kTH>
 __device__ __forceinline__ void staged_tile(const TcArgs& a, const float* bias_s, uint32_t stg, int q, int lane, int b, int tile_y,
-                                            int tile_x, uint32_t trow, bool lean_ok, bool vec_ok, float slope) {
+                                            int tile_x, uint32_t trow, bool lean_ok, bool vec_ok, float slope, int oy_off, int ox_off) {
     if (lean_ok) {
         const size_t esize = a.out_f16 ? 2 : 4;
         uint8_t* qptr[4];
@@ -278,7 +282,7 @@ __device__ __forceinline__ void staged_tile(const TcArgs& a, const float* bias_s
             const int pq = 32 * q + (lane >> 2) + 8 * k;
             const int qy = tile_y * kTH + pq / kTW, qx = tile_x * kTW + pq % kTW;
             qlive[k] = (qy < a.Ho) && (qx < a.Wo);
-            const size_t qidx = (((size_t)b * a.dst_H + (qy * a.oy_step + a.oy_off)) * a.dst_W + (qx * a.ox_step + a.ox_off)) *
+            const size_t qidx = (((size_t)b * a.dst_H + (qy * a.oy_step + oy_off)) * a.dst_W + (qx * a.ox_step + ox_off)) *
                                     a.dst_c + a.dst_coff;
             qptr[k] = reinterpret_cast<uint8_t*>(a.dst) + qidx * esize;
         }
@@ -288,10 +292,25 @@ __device__ __forceinline__ void staged_tile(const TcArgs& a, const float* bias_s
     } else {
         const int p = 32 * q + lane;
         const int oy = tile_y * kTH + p / kTW, ox = tile_x * kTW + p % kTW;
-        const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + a.oy_off)) * a.dst_W + (ox * a.ox_step + a.ox_off)) *
+        const size_t oidx = (((size_t)b * a.dst_H + (oy * a.oy_step + oy_off)) * a.dst_W + (ox * a.ox_step + ox_off)) *
                                 a.dst_c + a.dst_coff;
-        float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
-        epilogue_row_outofline(trow, a, bias_s, op, (oy < a.Ho) && (ox < a.Wo), vec_ok);
+        const bool live = (oy < a.Ho) && (ox < a.Wo);
+        if (a.Cout == 1) {
+            // single-channel heads (sigmoid / a + b |tanh|): one accumulator column per pixel instead of the generic path's 16
+            // activations per pixel (measured: 24->1 3x3 at full resolution 123 us with the generic epilogue)
+            uint32_t r;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(trow));
+            tmem_ld_wait();
+            float x = act_fn(__uint_as_float(r) + bias_s[0], a.act, a.act_a, a.act_b);
+            if (a.round_out) x = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+            if (live) {
+                if (a.out_f16) reinterpret_cast<__half*>(a.dst)[oidx] = __float2half_rn(x);
+                else a.dst[oidx] = x;
+            }
+        } else {
+            float* op = a.out_f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(a.dst) + oidx) : a.dst + oidx;
+            epilogue_row_outofline(trow, a, bias_s, op, live, vec_ok);
+        }
     }
 }
 
@@ -304,7 +323,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // main loop of tile i+1.
 __global__ void __launch_bounds__(kTcThreads)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB3, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * 8 + 4];   // full[8], empty[8], tmem_full[2], tmem_empty[2]
     __shared__ uint32_t tmem_base_s;
@@ -318,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
     const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
     const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
-    const int total = a.kh * a.kw * chunks_per_tap;
+    const int n_phase = a.n_phase;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -331,6 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (a.n_src > 1) prefetch_tmap(&tmA1);
         if (a.n_src > 2) prefetch_tmap(&tmA2);
         prefetch_tmap(&tmB);
+        if (n_phase > 1) { prefetch_tmap(&tmB1); prefetch_tmap(&tmB2); prefetch_tmap(&tmB3); }
     }
     if (warp == 1) {   // TMEM allocation (power of two >= 32 columns), address published through shared memory
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
@@ -347,12 +368,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+                const int sp = tile / n_phase, phs = tile - sp * n_phase;
+                const int b = sp / a.tiles_per_img, t = sp - b * a.tiles_per_img;
                 const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
                 const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
-                for (int ky = 0; ky < a.kh; ++ky)
-                    for (int kx = 0; kx < a.kw; ++kx) {
-                        const int ix0 = ox0 * a.sx - a.pad_l + kx, iy0 = oy0 * a.sy - a.pad_t + ky;
+                const int kh = a.ph_kh[phs], kw = a.ph_kw[phs], pad_t = a.ph_pad_t[phs], pad_l = a.ph_pad_l[phs];
+                const CUtensorMap* tb = (phs == 0) ? &tmB : ((phs == 1) ? &tmB1 : ((phs == 2) ? &tmB2 : &tmB3));
+                for (int ky = 0; ky < kh; ++ky)
+                    for (int kx = 0; kx < kw; ++kx) {
+                        const int ix0 = ox0 * a.sx - pad_l + kx, iy0 = oy0 * a.sy - pad_t + ky;
                         int kbase = 0;
                         for (int s = 0; s < a.n_src; ++s) {
                             const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
@@ -363,7 +387,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 const uint32_t sa = tile_base + st * stage_bytes, sb = sa + a_bytes;
                                 mbar_expect_tx(full0 + 8 * st, stage_bytes);
                                 tma_load_4d(sa, tm, full0 + 8 * st, j * a.kc, ix0, iy0, b);
-                                tma_load_2d(sb, &tmB, full0 + 8 * st, kbase + j * a.kc, (ky * a.kw + kx) * a.n_pad);
+                                tma_load_2d(sb, tb, full0 + 8 * st, kbase + j * a.kc, (ky * kw + kx) * a.n_pad);
                             }
                             kbase += a.chunks[s] * a.kc;
                         }
@@ -381,6 +405,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_d + (uint32_t)(buf * a.n_pad);
+            const int phs = tile % n_phase;
+            const int total = a.ph_kh[phs] * a.ph_kw[phs] * chunks_per_tap;
             for (int c = 0; c < total; ++c, ++it) {
                 const int st = it % stages;
                 const uint32_t ph = (uint32_t)(it / stages) & 1u;
@@ -412,13 +438,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const float slope = a.act == MR_ACT_LEAKY ? a.act_a : 1.0f;
         int lt = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
-            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+            const int sp = tile / n_phase, phs = tile - sp * n_phase;
+            const int b = sp / a.tiles_per_img, t = sp - b * a.tiles_per_img;
             const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
             const int buf = lt & 1;
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            staged_tile<kTileW, kTileH>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope);
+            staged_tile<kTileW, kTileH>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope, a.ph_oy_off[phs],
+                                        a.ph_ox_off[phs]);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -580,7 +608,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(tfull0 + 8 * buf, ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * a.n_pad);
-            staged_tile<8, 16>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope);
+            staged_tile<8, 16>(a, bias_s, stg, q, lane, b, tile_y, tile_x, trow, lean_ok, vec_ok, slope, a.oy_off, a.ox_off);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
@@ -613,9 +641,23 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream) {
+static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad, int k_pad, int round_out, void* stream) {
     MR_REQUIRE(desc != nullptr, "mr_conv2d_nhwc_tc: null descriptor");
-    const mr_conv_desc& d = *desc;
+    MR_REQUIRE(n_phases >= 1 && n_phases <= 4, "mr_conv2d_nhwc_tc_phases: 1..4 phases (got %d)", n_phases);
+    const mr_conv_desc& d = desc[0];
+    for (int p = 1; p < n_phases; ++p) {   // phases share everything but the filter (size, padding, weights) and the output offset
+        const mr_conv_desc& e = desc[p];
+        bool same = e.n_src == d.n_src && e.B == d.B && e.Hs == d.Hs && e.Ws == d.Ws && e.upsample2 == d.upsample2 && e.sy == d.sy &&
+                    e.sx == d.sx && e.Ho == d.Ho && e.Wo == d.Wo && e.Cout == d.Cout && e.bias == d.bias && e.dst == d.dst &&
+                    e.dst_H == d.dst_H && e.dst_W == d.dst_W && e.dst_c == d.dst_c && e.dst_coff == d.dst_coff &&
+                    e.oy_step == d.oy_step && e.ox_step == d.ox_step && e.act == d.act && e.act_a == d.act_a && e.act_b == d.act_b &&
+                    e.src_dtype == d.src_dtype && e.dst_dtype == d.dst_dtype;
+        for (int s = 0; same && s < d.n_src; ++s) same = e.src[s] == d.src[s] && e.src_c[s] == d.src_c[s];
+        MR_REQUIRE(same, "mr_conv2d_nhwc_tc_phases: phase %d differs from phase 0 in more than filter size, padding, weights and output offset", p);
+        MR_REQUIRE(e.weight && e.kh >= 1 && e.kw >= 1 && (e.Ho - 1) * e.oy_step + e.oy_off < e.dst_H && (e.Wo - 1) * e.ox_step + e.ox_off < e.dst_W,
+                   "mr_conv2d_nhwc_tc_phases: phase %d: bad filter / output placement", p);
+        MR_REQUIRE((reinterpret_cast<uintptr_t>(e.weight) & 15) == 0, "mr_conv2d_nhwc_tc_phases: weights are not 16-byte aligned");
+    }
     MR_REQUIRE(d.n_src >= 1 && d.n_src <= MR_CONV_MAX_SRC, "mr_conv2d_nhwc_tc: n_src=%d out of range", d.n_src);
     MR_REQUIRE(d.upsample2 == 0, "mr_conv2d_nhwc_tc: upsample-on-read is expressed as sub-pixel convolutions on this path");
     MR_REQUIRE(d.weight && d.dst, "mr_conv2d_nhwc_tc: null weight/dst");
@@ -678,7 +720,7 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, i
         return st > 4 ? 4 : st;
     };
     int halo_ctas = 0;
-    if (halo_env != 0 && (!f16 || halo_f16) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
+    if (n_phases == 1 && halo_env != 0 && (!f16 || halo_f16) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
         if (halo_env == 1 || halo_env == 2) halo_ctas = halo_fit(halo_env) >= 2 ? halo_env : 0;
         else if (halo_fit(2) >= 2) halo_ctas = 2;
     }
@@ -709,13 +751,14 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, i
     for (int s = d.n_src; s < MR_CONV_MAX_SRC; ++s) tmA[s] = tmA[0];
     MR_REQUIRE(ksum == k_pad, "mr_conv2d_nhwc_tc: packed weight K (%d) does not match the sources (%d)", k_pad, ksum);
     MR_REQUIRE((reinterpret_cast<uintptr_t>(d.weight) & 15) == 0, "mr_conv2d_nhwc_tc: weights are not 16-byte aligned");
-    CUtensorMap tmB;
-    {
-        const cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)d.kh * d.kw * n_pad};
+    CUtensorMap tmBs[4];
+    for (int p = 0; p < n_phases; ++p) {
+        const mr_conv_desc& e = desc[p];
+        const cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)e.kh * e.kw * n_pad};
         const cuuint64_t gstr[1] = {(cuuint64_t)k_pad * esize};
         const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_pad};
         const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmB, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d.weight), gdim, gstr, box, estr,
+        CUresult r = encode(&tmBs[p], f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(e.weight), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -723,13 +766,20 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, i
             return MR_EINVAL;
         }
     }
+    for (int p = n_phases; p < 4; ++p) tmBs[p] = tmBs[0];
+    const CUtensorMap& tmB = tmBs[0];
+    a.n_phase = n_phases;
+    for (int p = 0; p < 4; ++p) {
+        const mr_conv_desc& e = desc[p < n_phases ? p : 0];
+        a.ph_kh[p] = e.kh; a.ph_kw[p] = e.kw; a.ph_pad_t[p] = e.pad_t; a.ph_pad_l[p] = e.pad_l; a.ph_oy_off[p] = e.oy_off; a.ph_ox_off[p] = e.ox_off;
+    }
     a.kh = d.kh; a.kw = d.kw; a.sy = d.sy; a.sx = d.sx; a.pad_t = d.pad_t; a.pad_l = d.pad_l;
     a.Ho = d.Ho; a.Wo = d.Wo; a.Cout = d.Cout; a.n_pad = n_pad;
     a.tiles_x = halo ? (d.Wo + 7) / 8 : (d.Wo + kTileW - 1) / kTileW;
     const int tiles = a.tiles_x * (halo ? (d.Ho + 15) / 16 : (d.Ho + kTileH - 1) / kTileH);
     const size_t stage_bytes = (size_t)(128 + n_pad) * a.row_bytes;
     a.tiles_per_img = tiles;
-    a.total_tiles = tiles * d.B;
+    a.total_tiles = tiles * d.B * n_phases;
     // persistent grid: two CTAs per SM when two double-buffered accumulators fit TMEM (2 x 2 x n_pad <= 512 columns),
     // otherwise one CTA per SM with a deeper ring
     int dev = 0, sms = 148;
@@ -776,11 +826,15 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_pad, int k_pad, i
     int grid = sms * ctas_per_sm;
     if (grid > a.total_tiles) grid = a.total_tiles;
     MR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(212 * 1024)));
-    conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmB, a);
+    conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA[0], tmA[1], tmA[2], tmBs[0], tmBs[1], tmBs[2], tmBs[3], a);
     MR_LAUNCH_CHECK("conv_tc_kernel");
     return MR_OK;
 }
 
 extern "C" int mr_conv2d_nhwc_tc(const mr_conv_desc* desc, int n_pad, int k_pad, int round_out, void* stream) {
-    return conv2d_nhwc_tc_impl(desc, n_pad, k_pad, round_out, stream);
+    return conv2d_nhwc_tc_impl(desc, 1, n_pad, k_pad, round_out, stream);
+}
+
+extern "C" int mr_conv2d_nhwc_tc_phases(const mr_conv_desc* descs, int n_phases, int n_pad, int k_pad, int round_out, void* stream) {
+    return conv2d_nhwc_tc_impl(descs, n_phases, n_pad, k_pad, round_out, stream);
 }

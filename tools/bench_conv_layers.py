@@ -52,3 +52,22 @@ for name, B, H, W, src_c, cout, kh, kw in cases:
     flops = 2.0 * B * H * W * sum(src_c) * cout * kh * kw
     byts = (2.0 if half else 4.0) * B * H * W * (sum(src_c) + cout)
     print(f"{name:40s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s  {byts / us / 1e3:7.1f} GB/s (in+out)")
+
+# sub-pixel layers (four phases): Refine = ConvTranspose2d(k4, s2) + crop, Upconv = nearest x2 + 2x2 conv
+for name, B, H, W, src_c, cout, kind in [("refine 64+64+64->48 B8 1/2", 8, 128, 256, (64, 64, 64), 48, "refine"),
+                                         ("refine 128+64+128->64 B8 1/4", 8, 64, 128, (128, 64, 128), 64, "refine"),
+                                         ("refine 192+128+256->128 B8 1/8", 8, 32, 64, (192, 128, 256), 128, "refine"),
+                                         ("refine 256->256 B8 1/16", 8, 16, 32, (256,), 256, "refine"),
+                                         ("upconv 64->64 B8 1/2", 8, 128, 256, (64,), 64, "upconv"),
+                                         ("upconv 96->96 B8 1/4", 8, 64, 128, (96,), 96, "upconv")]:
+    xs = [torch.randn(B, H, W, c, device=dev) for c in src_c]
+    if half:
+        xs = [x.half() for x in xs]
+    if kind == "refine":
+        L = C.refine_layer(torch.nn.ConvTranspose2d(sum(src_c), cout, 4, 2).to(dev), src_c)
+    else:
+        L = C.upconv_layer(torch.nn.Conv2d(sum(src_c), cout, 2).to(dev), src_c)
+    us = timed(lambda: L(xs))
+    es = 2.0 if half else 4.0
+    byts = es * B * H * W * (sum(src_c) + 4 * cout)
+    print(f"{name:40s} {us:8.1f} us  {byts / us / 1e3:7.1f} GB/s (in once + out)")
