@@ -701,10 +701,10 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad
     int chunks_all = 0;
     for (int s = 0; s < d.n_src; ++s) chunks_all += (d.src_c[s] + kc - 1) / kc;
     const size_t bres = (size_t)d.kh * d.kw * chunks_all * n_pad * a.row_bytes;
-    // MONOREC_B200_TC_HALO: unset = automatic, 0 = never, 1 / 2 = always when eligible with that many CTAs per SM.
-    // Automatic (measured on the stacks' layers): only when weights + two halo stages fit twice per SM, i.e. two CTAs per
-    // SM (32->32 3x3 over the single-frame volumes: 631 -> 452 us in TF32, 489 -> 429 us in half); with a single CTA per SM
-    // its four epilogue warps become the bottleneck (48->48 3x3: 300 -> 335 us), so those layers keep the tap-refetch kernel.
+    // MONOREC_B200_TC_HALO: unset = automatic, 0 = never, n = 1..4: at most n CTAs per SM (1: also layers that only fit once).
+    // History of the rule: with 16-px box rows only the 32-channel layers fitted twice per SM (32->32 3x3 over the single-frame
+    // volumes: 631 -> 452 us in TF32, 489 -> 203 us in half) and one CTA per SM lost to the tap-refetch kernel (48->48 3x3:
+    // 300 -> 335 us); with (8 + kw - 1)-px rows the 48-channel full-resolution layers fit twice as well (profiles/r02_k2_pitch.txt).
     static const int halo_env = getenv("MONOREC_B200_TC_HALO") ? atoi(getenv("MONOREC_B200_TC_HALO")) : -1;
     static const bool halo_f16 = getenv("MONOREC_B200_TC_HALO_F16") ? (atoi(getenv("MONOREC_B200_TC_HALO_F16")) != 0) : true;
     // (64-byte rows are fine inside the halo box too: half sources of <= 32 channels packed with 32-channel chunks; measured
@@ -714,15 +714,24 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad
     const int halo_pitch = (pitch_env >= 8 + d.kw - 1) ? pitch_env : 8 + d.kw - 1;
     const size_t halo_a_bytes = ((size_t)(16 + d.kh - 1) * halo_pitch * a.row_bytes + 1023) & ~size_t(1023);
     const size_t bres_al = (bres + 1023) & ~size_t(1023);
-    auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights (228 KB per SM, 1 KB reserved + ~1.1 KB static per CTA)
-        const size_t budget = (size_t)(ctas == 2 ? 224 : 210) * 1024 / ctas - 8 * 1024;   // 8 KB: the epilogue's staging buffers (static)
-        int st = bres_al + 2048 < budget ? (int)((budget - 2048 - bres_al) / halo_a_bytes) : 0;
+    uint32_t halo_cols = 32;               // TMEM columns one CTA allocates (two accumulators)
+    while (halo_cols < (uint32_t)(2 * n_pad)) halo_cols <<= 1;
+    auto halo_fit = [&](int ctas) {   // A stages that fit next to the resident weights with `ctas` CTAs per SM
+        if ((uint32_t)ctas * halo_cols > 512) return 0;
+        // 228 KB per SM, 1 KB reserved per CTA; static per CTA: 8 KB epilogue staging + 1 KB bias + barriers; 1 KB alignment slack
+        const size_t budget = (size_t)(ctas == 1 ? 210 : 228) * 1024 / ctas - (1 + 8 + 1 + 1) * 1024 - 512;
+        int st = bres_al + 1024 < budget ? (int)((budget - 1024 - bres_al) / halo_a_bytes) : 0;
         return st > 4 ? 4 : st;
     };
+    // CTAs per SM: two, each with as many input stages as fit (up to 4).  Measured (profiles/r02_k2_ctas.txt): allowing 3 or 4
+    // CTAs per SM leaves each only 2 stages and is slower (3x1 48->48 at full resolution 50 -> 70 us, half-mode forward
+    // 4.61 -> 4.72 / 4.88 ms): the prefetch depth matters more than the number of resident CTAs.
+    // MONOREC_B200_TC_HALO=n (1..4) caps / forces the count for measurements (1: also layers that only fit once).
     int halo_ctas = 0;
     if (n_phases == 1 && halo_env != 0 && (!f16 || halo_f16) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
-        if (halo_env == 1 || halo_env == 2) halo_ctas = halo_fit(halo_env) >= 2 ? halo_env : 0;
-        else if (halo_fit(2) >= 2) halo_ctas = 2;
+        const int cap = (halo_env >= 1 && halo_env <= 4) ? halo_env : 2;
+        for (int c = cap; c >= (halo_env == 1 ? 1 : 2) && halo_ctas == 0; --c)
+            if (halo_fit(c) >= 2) halo_ctas = c;
     }
     const bool halo = halo_ctas > 0;
     const int halo_stages = halo ? halo_fit(halo_ctas) : 0;
