@@ -471,6 +471,39 @@ def main():
         C.set_mode(default_mode)
         del model
 
+    # SURVEY 8f row 4 (informational, single-GPU runs): the photometric reprojection loss, forward and forward + backward
+    if world == 1 and not args.no_full_model:
+        try:
+            from monorec_b200 import losses as RL
+            invd = (0.15 + 0.1 * torch.rand(B, 1, H, W, device=dev)).requires_grad_(True)
+            rd = sets[0]
+
+            def _fwd():
+                with torch.no_grad():
+                    RL.reprojection_loss(invd, rd, automasking=True, reduce=False)
+
+            def _fwd_bwd():
+                invd.grad = None
+                RL.reprojection_loss(invd, rd, automasking=True, reduce=True).backward()
+
+            times = []
+            for fn in (_fwd, _fwd_bwd):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record()
+                for _ in range(20):
+                    fn()
+                r1.record()
+                torch.cuda.synchronize()
+                times.append(r0.elapsed_time(r1) / 20)
+            line["reprojection_loss"] = {"forward_ms": times[0], "forward_backward_ms": times[1], "batch": B, "frames": F,
+                                         "what": "monorec_b200.losses.reprojection_loss(automasking=True) on the bench inputs: "
+                                                 "mr_reprojection_loss_fwd / _bwd through autograd (eager, incl. mr_projection_tables)"}
+        except Exception as exc:   # noqa: BLE001
+            line["reprojection_loss_error"] = f"{type(exc).__name__}: {exc}"[:200]
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores = cpu_port_keyframes_per_s(repeats=2)
         line["cpu_baseline"] = {"value": v, "unit": "keyframes/s", "cores": cores, "kind": "port",

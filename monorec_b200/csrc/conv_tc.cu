@@ -23,6 +23,7 @@
 #include "mr_common.cuh"
 #include <cuda.h>
 #include <cstdint>
+#include <type_traits>
 #include <cstdlib>
 #include <cuda_fp16.h>
 
@@ -34,7 +35,9 @@ constexpr int kTileH = 8, kTileW = 16;  // 128 output pixels per CTA
 
 struct TcArgs {
     int n_src;
-    int chunks[MR_CONV_MAX_SRC];   // 32-channel chunks per source
+    int chunks[MR_CONV_MAX_SRC];   // K chunks per source
+    int tail_ksteps[MR_CONV_MAX_SRC];   // MMA K steps (32 bytes of channels each) that hold data in the LAST chunk of each source: the
+                                        // zero padding behind a source's channels is neither multiplied nor read from shared memory
     int kh, kw, sy, sx, pad_t, pad_l;
     int Ho, Wo, Cout, n_pad, tiles_x, tiles_per_img, total_tiles, stages;
     uint32_t tmem_cols;
@@ -53,6 +56,8 @@ struct TcArgs {
     // index = spatial tile * n_phase + phase, so the phases of a spatial tile run side by side and its input boxes are L2 hits
     int n_phase;
     int ph_kh[4], ph_kw[4], ph_pad_t[4], ph_pad_l[4], ph_oy_off[4], ph_ox_off[4];
+    int b_stream;                  // halo kernel: 0 = the layer's weights stay resident in shared memory; n > 0 = they do not fit: the
+                                   // [n_pad x chunk] slice of every (chunk, tap) streams through a ring of n stages instead
     int halo_pitch;                // halo kernel: pixels per input row of the shared-memory box (8 outputs + kw - 1 taps to the right)
     uint32_t halo_a_bytes;         // halo kernel: bytes of one input stage (box rounded up to 1 KB)
 };
@@ -62,9 +67,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -78,18 +80,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -97,27 +87,83 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major) |
 //   [32,46) stride byte offset >> 4 (distance between 8-row groups) | [46,48) version = 1 | [49,52) base offset |
 //   [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.  Everything but the start address is layer-constant: TcArgs::desc_hi.
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// ---- single-lane instructions issued from CONVERGED warp code ---------------------------------------------------------------
+// The producer and MMA warps used to run their loops under `if (lane == 0)`.  Every operand of UTMALDG / UTCHMMA / UTCBAR lives
+// in a uniform register, and inside a divergent region ptxas cannot keep values there: the SASS of the tap loop had ~20
+// instructions (R2UR.BROADCAST, ELECT, a waterfall branch) around every MMA, and that single-thread instruction stream -- not
+// the tensor pipe, shared memory or HBM -- paced the kernels.  Here all 32 lanes execute the loops (uniform arithmetic only) and
+// the instruction itself is predicated on elect.sync.
+template <bool F16>
+__device__ __forceinline__ void umma_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+    if (F16)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, pe;\n\t"
+            ".reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+            "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, pe;\n\t"
+            ".reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+            "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "}\n" ::"r"(bar), "r"(bytes)
         : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t"
+        "}\n" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t"
+        "}\n" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// shared-memory descriptor halves: low word = start address >> 4 | LBO (1, unused) << 16; high word = SBO >> 4 | version 1 << 14 |
+// layout << 29 (the K-major swizzled descriptor's bit layout is in the comment further up)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t row_bytes) {
+    return (sbo_bytes >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+}
+
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -330,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[256];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (the broadcast tells ptxas the role branches are warp-uniform)
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t a_bytes = 128u * (uint32_t)a.row_bytes, b_bytes = (uint32_t)a.n_pad * (uint32_t)a.row_bytes;
     const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -364,42 +410,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const uint32_t tmem_d = tmem_base_s;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int sp = tile / n_phase, phs = tile - sp * n_phase;
-                const int b = sp / a.tiles_per_img, t = sp - b * a.tiles_per_img;
-                const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
-                const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
-                const int kh = a.ph_kh[phs], kw = a.ph_kw[phs], pad_t = a.ph_pad_t[phs], pad_l = a.ph_pad_l[phs];
-                const CUtensorMap* tb = (phs == 0) ? &tmB : ((phs == 1) ? &tmB1 : ((phs == 2) ? &tmB2 : &tmB3));
-                for (int ky = 0; ky < kh; ++ky)
-                    for (int kx = 0; kx < kw; ++kx) {
-                        const int ix0 = ox0 * a.sx - pad_l + kx, iy0 = oy0 * a.sy - pad_t + ky;
-                        int kbase = 0;
-                        for (int s = 0; s < a.n_src; ++s) {
-                            const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
-                            for (int j = 0; j < a.chunks[s]; ++j, ++it) {
-                                const int st = it % stages;
-                                const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                                mbar_wait(empty0 + 8 * st, ph ^ 1u);
-                                const uint32_t sa = tile_base + st * stage_bytes, sb = sa + a_bytes;
-                                mbar_expect_tx(full0 + 8 * st, stage_bytes);
-                                tma_load_4d(sa, tm, full0 + 8 * st, j * a.kc, ix0, iy0, b);
-                                tma_load_2d(sb, tb, full0 + 8 * st, kbase + j * a.kc, (ky * kw + kx) * a.n_pad);
-                            }
-                            kbase += a.chunks[s] * a.kc;
+        // ===================== TMA producer (whole warp, converged; the copies are issued by an elected lane) =====================
+        int st = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            const int sp = tile / n_phase, phs = tile - sp * n_phase;
+            const int b = sp / a.tiles_per_img, t = sp - b * a.tiles_per_img;
+            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+            const int oy0 = tile_y * kTileH, ox0 = tile_x * kTileW;
+            const int kh = a.ph_kh[phs], kw = a.ph_kw[phs], pad_t = a.ph_pad_t[phs], pad_l = a.ph_pad_l[phs];
+            const CUtensorMap* tb = (phs == 0) ? &tmB : ((phs == 1) ? &tmB1 : ((phs == 2) ? &tmB2 : &tmB3));
+            int brow = 0;
+            for (int ky = 0; ky < kh; ++ky)
+                for (int kx = 0; kx < kw; ++kx, brow += a.n_pad) {
+                    const int ix0 = ox0 * a.sx - pad_l + kx, iy0 = oy0 * a.sy - pad_t + ky;
+                    int kbase = 0;
+                    for (int s = 0; s < a.n_src; ++s) {
+                        const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
+                        for (int j = 0; j < a.chunks[s]; ++j, kbase += a.kc) {
+                            mbar_wait(empty0 + 8 * st, ph ^ 1u);
+                            const uint32_t sa = tile_base + st * stage_bytes, sb = sa + a_bytes;
+                            mbar_expect_tx_elect(full0 + 8 * st, stage_bytes);
+                            tma_load_4d_elect(sa, tm, full0 + 8 * st, j * a.kc, ix0, iy0, b);
+                            tma_load_2d_elect(sb, tb, full0 + 8 * st, kbase, brow);
+                            if (++st == stages) { st = 0; ph ^= 1u; }
                         }
                     }
-            }
+                }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (whole warp, converged; the MMAs are issued by an elected lane) =====================
         // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6), a/b format TF32 = 2 @[7,10)/[10,13),
         // K-major A and B, N >> 3 @[17,23), M >> 4 @[24,29)
         const uint32_t idesc = a.idesc;
-        int it = 0, lt = 0;
+        const uint32_t dhi = desc_hi(8u * (uint32_t)a.row_bytes, (uint32_t)a.row_bytes);
+        const int ksteps = a.row_bytes / 32;   // UMMA K = 32 bytes (8 tf32 / 16 half): 4 (2) steps inside the 128 (64)-byte swizzle row
+        auto run = [&](auto f16tag) {
+        constexpr bool kF16 = decltype(f16tag)::value;
+        int st = 0, lt = 0;
+        uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int buf = lt & 1;
             mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -407,26 +456,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t acc = tmem_d + (uint32_t)(buf * a.n_pad);
             const int phs = tile % n_phase;
             const int total = a.ph_kh[phs] * a.ph_kw[phs] * chunks_per_tap;
-            for (int c = 0; c < total; ++c, ++it) {
-                const int st = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            uint32_t accf = 0;
+            int src = 0, jc = 0;                                             // source / chunk inside the source of step c
+            for (int c = 0; c < total; ++c) {
                 mbar_wait(full0 + 8 * st, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t sa = tile_base + st * stage_bytes, sb = sa + a_bytes;
-                    const uint64_t da = (uint64_t)((sa & 0x3FFFF) >> 4) | a.desc_hi, db = (uint64_t)((sb & 0x3FFFF) >> 4) | a.desc_hi;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {   // UMMA K = 32 bytes (8 tf32 / 16 half): 4 (2) steps inside the 128 (64)-byte swizzle row
-                        if (32 * k >= a.row_bytes) break;
-                        if (a.f16) umma_f16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
-                        else       umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (c | k) ? 1u : 0u);
-                    }
-                    umma_commit(empty0 + 8 * st);                      // frees the smem stage once these MMAs have read it
-                    if (c == total - 1) umma_commit(tfull0 + 8 * buf); // accumulator complete
-                }
-                __syncwarp();
+                const uint32_t sa = tile_base + st * stage_bytes;
+                const uint32_t alo = desc_lo(sa), blo = desc_lo(sa + a_bytes);
+                const int ks = (jc == a.chunks[src] - 1) ? a.tail_ksteps[src] : ksteps;
+                umma_elect<kF16>(acc, alo, dhi, blo, dhi, idesc, accf);
+                if (ks > 1) umma_elect<kF16>(acc, alo + 2, dhi, blo + 2, dhi, idesc, 1u);
+                if (ks > 2) umma_elect<kF16>(acc, alo + 4, dhi, blo + 4, dhi, idesc, 1u);
+                if (ks > 3) umma_elect<kF16>(acc, alo + 6, dhi, blo + 6, dhi, idesc, 1u);
+                if (++jc == a.chunks[src]) { jc = 0; if (++src == a.n_src) src = 0; }
+                accf = 1u;
+                umma_commit_elect(empty0 + 8 * st);                          // frees the smem stage once these MMAs have read it
+                if (c == total - 1) umma_commit_elect(tfull0 + 8 * buf);     // accumulator complete
+                if (++st == stages) { st = 0; ph ^= 1u; }
             }
         }
+        };
+        if (a.f16) run(std::true_type{}); else run(std::false_type{});
     } else {
         // ===================== epilogue, staged through shared memory (see epilogue_staged) =====================
         __shared__ __align__(16) uint8_t stage_s[4][2048];
@@ -471,17 +521,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 //     L2->SM traffic drops from kh*kw boxes per tile to one.
 // Output tile = 16 rows x 8 columns (an 8-row MMA group = 8 adjacent pixels of one output row).
 // -------------------------------------------------------------------------------------------------------------------------
-#ifndef MR_HALO_BASE_OFFSET
-#define MR_HALO_BASE_OFFSET 0
-#endif
-__device__ __forceinline__ uint64_t make_desc_halo(uint32_t saddr, uint32_t row_bytes, uint32_t pitch) {
-    // K-major swizzled (128- or 64-byte rows), SBO = one halo row (`pitch` px), base offset 0: the swizzle is a function of the
-    // absolute shared-memory address; MR_HALO_BASE_OFFSET=1 restores the row-phase variant for experiments
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((pitch * row_bytes) >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)(MR_HALO_BASE_OFFSET ? ((saddr >> 7) & 7) : 0) << 49) |
-           ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
-}
-
 // ROWB: bytes per shared-memory row, 128 or 64 (half sources of <= 32 channels)
 template <int ROWB>
 __global__ void __launch_bounds__(kTcThreads)
@@ -489,17 +528,20 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int kBufs = 2;                                     // TMEM accumulators (double-buffered)
-    __shared__ __align__(8) uint64_t bars[2 * 4 + 2 * kBufs + 1];   // afull[4], aempty[4], tmem_full[kBufs], tmem_empty[kBufs], bfull
+    // afull[4], aempty[4], tmem_full[kBufs], tmem_empty[kBufs], bfull, streamed weights: bsfull[8], bsempty[8]
+    __shared__ __align__(8) uint64_t bars[2 * 4 + 2 * kBufs + 1 + 16];
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[256];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (the broadcast tells ptxas the role branches are warp-uniform)
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t row_bytes = (uint32_t)ROWB;
     const uint32_t b_bytes = (uint32_t)a.n_pad * row_bytes;
     const int chunks_per_tap = a.chunks[0] + a.chunks[1] + a.chunks[2];
     const int taps = a.kh * a.kw;
-    const uint32_t bres_bytes = (uint32_t)(taps * chunks_per_tap) * b_bytes;       // multiple of 1024 (n_pad % 16 == 0)
+    const int nbs = a.b_stream;                                                    // weight ring stages (0: resident)
+    // bytes in front of the input stages: all weights, or the ring (multiple of 1024: n_pad % 16 == 0)
+    const uint32_t bres_bytes = (uint32_t)(nbs > 0 ? nbs : taps * chunks_per_tap) * b_bytes;
     const uint32_t a_bytes = a.halo_a_bytes;                                       // multiple of 1024
     const uint32_t pitch = (uint32_t)a.halo_pitch;
     const uint32_t a_tx = (uint32_t)(16 + a.kh - 1) * pitch * row_bytes;           // bytes one box delivers
@@ -507,11 +549,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int stages = a.stages;
     const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[4]);
     const uint32_t tfull0 = smem_u32(&bars[8]), tempty0 = smem_u32(&bars[8 + kBufs]), bfull = smem_u32(&bars[8 + 2 * kBufs]);
+    const uint32_t bsfull0 = smem_u32(&bars[9 + 2 * kBufs]), bsempty0 = smem_u32(&bars[17 + 2 * kBufs]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
         for (int s = 0; s < kBufs; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
         mbar_init(bfull, 1);
+        for (int s = 0; s < nbs; ++s) { mbar_init(bsfull0 + 8 * s, 1); mbar_init(bsempty0 + 8 * s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 256; i += kTcThreads) bias_s[i] = (a.bias != nullptr && i < a.Cout) ? __ldg(a.bias + i) : 0.f;
@@ -532,65 +576,94 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint32_t tmem_d = tmem_base_s;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            // resident weights: every (tap, chunk) slice [n_pad x 32] once
-            mbar_expect_tx(bfull, bres_bytes);
+        // ===================== TMA producer (whole warp, converged; the copies are issued by an elected lane) =====================
+        // resident weights: every (tap, chunk) slice [n_pad x chunk] once
+        if (nbs == 0) {
+            mbar_expect_tx_elect(bfull, bres_bytes);
             for (int tp = 0; tp < taps; ++tp)
                 for (int cg = 0; cg < chunks_per_tap; ++cg)
-                    tma_load_2d(base + (uint32_t)(tp * chunks_per_tap + cg) * b_bytes, &tmB, bfull, cg * a.kc, tp * a.n_pad);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
-                const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
-                const int ix0 = tile_x * 8 - a.pad_l, iy0 = tile_y * 16 - a.pad_t;
-                for (int s = 0; s < a.n_src; ++s) {
-                    const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
-                    for (int j = 0; j < a.chunks[s]; ++j, ++it) {
-                        const int st = it % stages;
-                        const uint32_t ph = (uint32_t)(it / stages) & 1u;
-                        mbar_wait(aempty0 + 8 * st, ph ^ 1u);
-                        mbar_expect_tx(afull0 + 8 * st, a_tx);
-                        tma_load_4d(a_base + st * a_bytes, tm, afull0 + 8 * st, j * a.kc, ix0, iy0, b);
+                    tma_load_2d_elect(base + (uint32_t)(tp * chunks_per_tap + cg) * b_bytes, &tmB, bfull, cg * a.kc, tp * a.n_pad);
+        }
+        int st = 0, bs = 0;
+        uint32_t ph = 0, bph = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            const int b = tile / a.tiles_per_img, t = tile - b * a.tiles_per_img;
+            const int tile_y = t / a.tiles_x, tile_x = t - tile_y * a.tiles_x;
+            const int ix0 = tile_x * 8 - a.pad_l, iy0 = tile_y * 16 - a.pad_t;
+            int kbase = 0;
+            for (int s = 0; s < a.n_src; ++s) {
+                const CUtensorMap* tm = (s == 0) ? &tmA0 : ((s == 1) ? &tmA1 : &tmA2);
+                for (int j = 0; j < a.chunks[s]; ++j, kbase += a.kc) {
+                    mbar_wait(aempty0 + 8 * st, ph ^ 1u);
+                    mbar_expect_tx_elect(afull0 + 8 * st, a_tx);
+                    tma_load_4d_elect(a_base + st * a_bytes, tm, afull0 + 8 * st, j * a.kc, ix0, iy0, b);
+                    if (++st == stages) { st = 0; ph ^= 1u; }
+                    if (nbs > 0) {   // streamed weights: the slices of this chunk, tap by tap, behind its input box
+                        int brow = 0;
+                        for (int tp = 0; tp < taps; ++tp, brow += a.n_pad) {
+                            mbar_wait(bsempty0 + 8 * bs, bph ^ 1u);
+                            mbar_expect_tx_elect(bsfull0 + 8 * bs, b_bytes);
+                            tma_load_2d_elect(base + (uint32_t)bs * b_bytes, &tmB, bsfull0 + 8 * bs, kbase, brow);
+                            if (++bs == nbs) { bs = 0; bph ^= 1u; }
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer (whole warp, converged; the MMAs are issued by an elected lane) =====================
         const uint32_t idesc = a.idesc;
-        mbar_wait(bfull, 0);
-        int it = 0, lt = 0;
+        const uint32_t dhi_a = desc_hi(pitch * row_bytes, row_bytes);      // stride between 8-row groups = one halo row
+        const uint32_t dhi_b = desc_hi(8u * row_bytes, row_bytes);
+        const uint32_t tap_dx = row_bytes >> 4, tap_dy = (pitch * row_bytes) >> 4;   // descriptor steps of one tap to the right / down
+        const uint32_t b_step = b_bytes >> 4;
+        if (nbs == 0) mbar_wait(bfull, 0);
+        auto run = [&](auto f16tag) {
+        constexpr bool kF16 = decltype(f16tag)::value;
+        int st = 0, bs = 0, lt = 0;
+        uint32_t ph = 0, bph = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++lt) {
             const int buf = lt & (kBufs - 1);
             mbar_wait(tempty0 + 8 * buf, (((uint32_t)lt >> 1) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_d + (uint32_t)(buf * a.n_pad);
-            for (int cg = 0; cg < chunks_per_tap; ++cg, ++it) {
-                const int st = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1u;
+            uint32_t accf = 0;
+            int src = 0, jc = 0;                                             // source / chunk inside the source of chunk cg
+            for (int cg = 0; cg < chunks_per_tap; ++cg) {
+                const int ks = (jc == a.chunks[src] - 1) ? a.tail_ksteps[src] : ROWB / 32;
+                if (++jc == a.chunks[src]) { jc = 0; ++src; }
                 mbar_wait(afull0 + 8 * st, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t sa = a_base + st * a_bytes;
-                    for (int ky = 0; ky < a.kh; ++ky)
-                        for (int kx = 0; kx < a.kw; ++kx) {
-                            const uint64_t da = make_desc_halo(sa + ((uint32_t)ky * pitch + (uint32_t)kx) * row_bytes, row_bytes, pitch);
-                            const uint32_t sb = base + (uint32_t)((ky * a.kw + kx) * chunks_per_tap + cg) * b_bytes;
-                            const uint64_t db = (uint64_t)((sb & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) |
-                                                ((uint64_t)1 << 46) | ((uint64_t)(row_bytes == 128 ? 2 : 4) << 61);
-#pragma unroll
-                            for (int k = 0; k < ROWB / 32; ++k) {   // 32 bytes of K per MMA (8 tf32 / 16 half): 4 per 128-byte row, 2 per 64-byte row
-                                if (a.f16) umma_f16(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
-                                else       umma_tf32(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (cg | ky | kx | k) ? 1u : 0u);
-                            }
+                uint32_t alo_row = desc_lo(a_base + st * a_bytes);
+                uint32_t blo = desc_lo(base) + (uint32_t)cg * b_step;                 // resident: slice (tap 0, chunk cg)
+                for (int ky = 0; ky < a.kh; ++ky, alo_row += tap_dy) {
+                    uint32_t alo = alo_row;
+                    for (int kx = 0; kx < a.kw; ++kx, alo += tap_dx) {
+                        if (nbs > 0) {
+                            mbar_wait(bsfull0 + 8 * bs, bph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            blo = desc_lo(base + (uint32_t)bs * b_bytes);
                         }
-                    umma_commit(aempty0 + 8 * st);
-                    if (cg == chunks_per_tap - 1) umma_commit(tfull0 + 8 * buf);
+#pragma unroll
+                        for (int k = 0; k < ROWB / 32; ++k) {   // 32 bytes of K per MMA (8 tf32 / 16 half): 4 per 128-byte row, 2 per 64-byte row
+                            if (k < ks) umma_elect<kF16>(acc, alo + 2 * k, dhi_a, blo + 2 * k, dhi_b, idesc, accf);
+                            accf = 1u;
+                        }
+                        if (nbs > 0) {
+                            umma_commit_elect(bsempty0 + 8 * bs);   // frees the weight stage once these MMAs have read it
+                            if (++bs == nbs) { bs = 0; bph ^= 1u; }
+                        } else {
+                            blo += (uint32_t)chunks_per_tap * b_step;   // next tap, same chunk
+                        }
+                    }
                 }
-                __syncwarp();
+                umma_commit_elect(aempty0 + 8 * st);
+                if (cg == chunks_per_tap - 1) umma_commit_elect(tfull0 + 8 * buf);
+                if (++st == stages) { st = 0; ph ^= 1u; }
             }
         }
+        };
+        if (a.f16) run(std::true_type{}); else run(std::false_type{});
     } else {
         // ===================== epilogue, staged through shared memory (tile = 16 rows x 8 columns) =====================
         __shared__ __align__(16) uint8_t stage_s[4][2048];
@@ -733,8 +806,28 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad
         for (int c = cap; c >= (halo_env == 1 ? 1 : 2) && halo_ctas == 0; --c)
             if (halo_fit(c) >= 2) halo_ctas = c;
     }
+    // Weights that do not fit next to two input stages stream instead: the [n_pad x chunk] slice of each (chunk, tap) goes through
+    // a ring of 3..8 stages behind the chunk's input box.  Per tile that is all the weights once (L2 hits) plus ONE input box per
+    // chunk, against kh*kw input boxes + the same weights in the tap-refetch kernel -- the multi-source decoder layers were bound
+    // by that L2->SM traffic (~12.7 TB/s aggregate on the 32+64->48 3x3 layer).  MONOREC_B200_TC_STREAM=0 disables it (A/B).
+    static const bool stream_on = getenv("MONOREC_B200_TC_STREAM") ? (atoi(getenv("MONOREC_B200_TC_STREAM")) != 0) : true;
+    int b_stream = 0, stream_stages = 0;
+    const size_t b_slice = (size_t)n_pad * a.row_bytes;
+    if (halo_ctas == 0 && stream_on && n_phases == 1 && halo_env != 0 && (!f16 || halo_f16) && d.sy == 1 && d.sx == 1 && d.kw <= 9 &&
+        d.kh <= 7 && d.kh * d.kw > 1 && 2 * halo_cols <= 512) {
+        const size_t budget = (size_t)228 * 1024 / 2 - (1 + 8 + 1 + 1) * 1024 - 512 - 1024;
+        if (budget > 2 * halo_a_bytes + 3 * b_slice) {
+            int nb = (int)((budget - 2 * halo_a_bytes) / b_slice);
+            if (nb > 8) nb = 8;
+            int st = (int)((budget - (size_t)nb * b_slice) / halo_a_bytes);
+            b_stream = nb;
+            stream_stages = st > 4 ? 4 : st;
+            halo_ctas = 2;
+        }
+    }
     const bool halo = halo_ctas > 0;
-    const int halo_stages = halo ? halo_fit(halo_ctas) : 0;
+    const int halo_stages = b_stream ? stream_stages : (halo ? halo_fit(halo_ctas) : 0);
+    const size_t halo_front = b_stream ? (size_t)b_stream * b_slice : bres_al;   // bytes in front of the input stages
     CUtensorMap tmA[MR_CONV_MAX_SRC];
     for (int s = 0; s < d.n_src; ++s) {
         const int C = d.src_c[s];
@@ -742,6 +835,7 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad
                    "mr_conv2d_nhwc_tc: source %d needs a channel count that is a multiple of %d (got %d)", s, cmult, C);
         MR_REQUIRE((reinterpret_cast<uintptr_t>(d.src[s]) & 15) == 0, "mr_conv2d_nhwc_tc: source %d is not 16-byte aligned", s);
         a.chunks[s] = (C + kc - 1) / kc;
+        a.tail_ksteps[s] = ((C - (a.chunks[s] - 1) * kc) * esize + 31) / 32;
         ksum += a.chunks[s] * kc;
         const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)d.Ws, (cuuint64_t)d.Hs, (cuuint64_t)d.B};
         const cuuint64_t gstr[3] = {(cuuint64_t)C * esize, (cuuint64_t)d.Ws * C * esize, (cuuint64_t)d.Hs * d.Ws * C * esize};
@@ -818,7 +912,8 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad
         a.stages = halo_stages;
         a.halo_pitch = halo_pitch;
         a.halo_a_bytes = (uint32_t)halo_a_bytes;
-        const size_t smem = bres_al + (size_t)halo_stages * halo_a_bytes + 1024;
+        a.b_stream = b_stream;
+        const size_t smem = halo_front + (size_t)halo_stages * halo_a_bytes + 1024;
         int grid = sms * halo_ctas;
         if (grid > a.total_tiles) grid = a.total_tiles;
         auto launch_halo = [&](auto kernel, int threads) -> int {

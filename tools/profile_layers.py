@@ -39,7 +39,15 @@ def halo_kind(L, half, n_pad):
     a = ((16 + L.kh - 1) * (8 + L.kw - 1) * row + 1023) // 1024 * 1024
     budget = 224 * 1024 // 2 - 8 * 1024
     st = (budget - 2048 - bres) // a if bres + 2048 < budget else 0
-    return f"halo x{min(st, 4)}" if st >= 2 else "refetch"
+    if st >= 2:
+        return f"halo x{min(st, 4)}"
+    cols = 32
+    while cols < 2 * n_pad:
+        cols *= 2
+    bud = 228 * 1024 // 2 - 11 * 1024 - 512 - 1024
+    if L.kh * L.kw > 1 and 2 * cols <= 512 and bud > 2 * a + 3 * n_pad * row:
+        return f"halo stream x{min(8, (bud - 2 * a) // (n_pad * row))}"
+    return "refetch"
 
 
 def wrapped(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f32=False, out_coff=0):
