@@ -796,13 +796,13 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad
         int st = bres_al + 1024 < budget ? (int)((budget - 1024 - bres_al) / halo_a_bytes) : 0;
         return st > 4 ? 4 : st;
     };
-    // CTAs per SM: two, each with as many input stages as fit (up to 4).  Measured (profiles/r02_k2_ctas.txt): allowing 3 or 4
-    // CTAs per SM leaves each only 2 stages and is slower (3x1 48->48 at full resolution 50 -> 70 us, half-mode forward
-    // 4.61 -> 4.72 / 4.88 ms): the prefetch depth matters more than the number of resident CTAs.
+    // CTAs per SM: up to three, each with at least two input stages (up to 4).  Measured after the issue loops moved to the
+    // uniform datapath (profiles/r02_k2_ctas2.txt): cap 2 / 3 / 4 -> half-mode forward 3.98 / 3.94 / 4.06 ms, 32->32 3x3 over
+    // the single-frame volumes 159 / 143 / 193 us (before that change 3-4 CTAs were slower than 2: profiles/r02_k2_ctas.txt).
     // MONOREC_B200_TC_HALO=n (1..4) caps / forces the count for measurements (1: also layers that only fit once).
     int halo_ctas = 0;
     if (n_phases == 1 && halo_env != 0 && (!f16 || halo_f16) && d.sy == 1 && d.sx == 1 && d.kw <= 9 && d.kh <= 7) {
-        const int cap = (halo_env >= 1 && halo_env <= 4) ? halo_env : 2;
+        const int cap = (halo_env >= 1 && halo_env <= 4) ? halo_env : 3;
         for (int c = cap; c >= (halo_env == 1 ? 1 : 2) && halo_ctas == 0; --c)
             if (halo_fit(c) >= 2) halo_ctas = c;
     }

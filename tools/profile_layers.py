@@ -67,7 +67,26 @@ def wrapped(srcs, L, out=None, out_hw=None, round_out=True, half=False, out_f32=
     return r
 
 
+orig_ph = C.conv2d_tc_phases
+
+
+def wrapped_phases(srcs, subs, out, out_hw, round_out=True, half=False):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = orig_ph(srcs, subs, out, out_hw, round_out=round_out, half=half)
+    e1.record()
+    Bn, Hs, Ws, _ = srcs[0].shape
+    L = subs[0]
+    es = 2 if half else 4
+    byts = Bn * Hs * Ws * sum(L.src_c) * es + r.numel() * r.element_size()
+    flops = sum(2.0 * Bn * Hs * Ws * S.cout * sum(S.src_c) * S.kh * S.kw for S in subs)
+    records.append((e0, e1, f"{'+'.join(map(str, L.src_c))}->{L.cout} {len(subs)} sub-pixel phases B{Bn} {Hs}x{Ws}", byts, flops,
+                    "refetch, one launch"))
+    return r
+
+
 C.conv2d_tc = wrapped
+C.conv2d_tc_phases = wrapped_phases
 with torch.no_grad():
     for _ in range(3):
         records.clear()
