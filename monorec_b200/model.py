@@ -23,6 +23,8 @@ __all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "Res
 # without casts (0.82 -> 0.71 ms at B=8); MONOREC_B200_TRUNK=cudnn_f32 keeps it in fp32
 TRUNK_CUDNN_F16 = os.environ.get("MONOREC_B200_TRUNK", "cudnn_f16").lower() != "cudnn_f32"
 TRUNK_FUSED = os.environ.get("MONOREC_B200_TRUNK_FUSED", "1") != "0"
+# the trunk's 512-channel level (never consumed, see ResnetEncoder._forward_folded) on first use; 0: always computed
+TRUNK_LAZY_LEVEL4 = os.environ.get("MONOREC_B200_TRUNK_LAZY_LEVEL4", "1") != "0"
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -173,15 +175,27 @@ class ResnetEncoder(nn.Module):
             if fused:
                 return torch.cudnn_convolution_add_relu(t, w, z, 1.0, bias, [1, 1], [1, 1], [1, 1], 1)
             return F.conv2d(t, w, bias, padding=1).add_(z).relu_()
-        x = conv_relu(x, f["stem"][0], f["stem"][1], tuple(e.conv1.stride), tuple(e.conv1.padding))
-        self.features = [x]
-        x = e.maxpool(x)
-        for blocks in f["blocks"]:
+        def run_blocks(x, blocks):
             for (w1, b1), stride, (w2, b2), down in blocks:
                 idt = x if down is None else F.conv2d(x, down[0], down[1], stride=down[2])
                 out = conv_relu(x, w1, b1, tuple(stride), (1, 1))
                 x = conv_add_relu(out, w2, b2, idt)
-            self.features.append(x)
+            return x
+        x = conv_relu(x, f["stem"][0], f["stem"][1], tuple(e.conv1.stride), tuple(e.conv1.padding))
+        feats = [x]
+        x = e.maxpool(x)
+        for blocks in f["blocks"][:3]:
+            x = run_blocks(x, blocks)
+            feats.append(x)
+        # The 512-channel level (layer4, 23 % of the trunk's multiply-adds) has no consumer: the MaskModule reads levels 0-3
+        # (monorec_model.py:372-380), the DepthModule levels 0-2 (:545), and nothing else in the reference touches
+        # data_dict["image_features"].  It is computed when somebody asks for it.
+        if TRUNK_LAZY_LEVEL4:
+            last = f["blocks"][3]
+            self.features = _TrunkFeatures(feats, lambda t: run_blocks(t, last))
+        else:
+            feats.append(run_blocks(x, f["blocks"][3]))
+            self.features = feats
         return self.features
 
     def forward(self, input_image):
@@ -195,6 +209,62 @@ class ResnetEncoder(nn.Module):
         self.features.append(e.layer3(self.features[-1]))
         self.features.append(e.layer4(self.features[-1]))
         return self.features
+
+
+class _TrunkFeatures(list):
+    """`image_features` (monorec_model.py:118-129) with its last entry evaluated on first use.  Slices and indices below 4 --
+    everything the Mask / Depth modules do -- never trigger it; index 4 / -1, iteration, comparison, concatenation, copy do."""
+
+    def __init__(self, first_four, tail_fn):
+        super().__init__(list(first_four) + [None])
+        self._tail_fn = tail_fn
+
+    def _fill(self):
+        if list.__getitem__(self, 4) is None:
+            with torch.no_grad():
+                list.__setitem__(self, 4, self._tail_fn(list.__getitem__(self, 3)))
+
+    def reset_tail(self):
+        """After a CUDA-graph replay rewrote level 3 in place: the cached level 4 is stale."""
+        list.__setitem__(self, 4, None)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            if 4 in range(*i.indices(5)):
+                self._fill()
+        elif i in (4, -1):
+            self._fill()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._fill()
+        return list.__iter__(self)
+
+    def __reversed__(self):
+        self._fill()
+        return list.__reversed__(self)
+
+    def __add__(self, other):
+        self._fill()
+        return list(list.__iter__(self)) + list(other)
+
+    def __eq__(self, other):
+        self._fill()
+        return list.__eq__(self, other)
+
+    __hash__ = None
+
+    def __contains__(self, item):
+        self._fill()
+        return list.__contains__(self, item)
+
+    def copy(self):
+        self._fill()
+        return list(list.__iter__(self))
+
+    def __reduce__(self):
+        self._fill()
+        return (list, (list(list.__iter__(self)),))
 
 
 class MaskModule(nn.Module):
@@ -584,4 +654,7 @@ class GraphedMonoRec:
             else:
                 v.copy_(data[k], non_blocking=True)
         self.graph.replay()
+        feats = self.static_out.get("image_features")
+        if isinstance(feats, _TrunkFeatures):
+            feats.reset_tail()
         return self.static_out

@@ -221,3 +221,29 @@ def test_integration_monkey_patch_resolves_through_reference_config_parser():
                 sys.modules[k] = v
         if str(ref) in sys.path:
             sys.path.remove(str(ref))
+
+
+def test_trunk_unused_level_is_lazy_and_identical():
+    """The 512-channel trunk level has no consumer in the reference (monorec_model.py:372-380, :545 read levels 0-3): it is
+    evaluated on first use.  Slices / indices the Mask and Depth modules use do not trigger it; index 4, iteration and
+    concatenation do, with the same values as the eager evaluation."""
+    import monorec_b200.model as M
+    enc = M.ResnetEncoder(18, pretrained=False).eval()
+    x = torch.rand(2, 3, 64, 128)
+    old = M.TRUNK_LAZY_LEVEL4
+    try:
+        with torch.no_grad():
+            M.TRUNK_LAZY_LEVEL4 = False
+            eager = enc(x)
+            M.TRUNK_LAZY_LEVEL4 = True
+            lazy = enc(x)
+        assert type(eager) is list and isinstance(lazy, M._TrunkFeatures) and len(lazy) == 5
+        assert len(lazy[:4]) == 4 and lazy[3].shape[1] == 256 and list.__getitem__(lazy, 4) is None      # not evaluated yet
+        assert torch.equal(lazy[4], eager[4]) and torch.equal(lazy[-1], eager[4])
+        with torch.no_grad():
+            lazy2 = enc(x)
+        assert all(torch.equal(a, b) for a, b in zip(lazy2, eager))                                        # iteration evaluates
+        lazy2.reset_tail()
+        assert list.__getitem__(lazy2, 4) is None and torch.equal((lazy2 + [])[4], eager[4])
+    finally:
+        M.TRUNK_LAZY_LEVEL4 = old
