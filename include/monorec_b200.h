@@ -197,6 +197,11 @@ int mr_nchw_to_nhwc_f16(const float* src, void* dst, int B, int C, int H, int W,
                         const float* one_minus_scale, void* stream);
 int mr_maxpool2_nhwc_f16(const void* src, void* dst, int B, int H, int W, int C, void* stream);
 int mr_max_over_frames_f16(const void* src, void* dst, int F, long long n_per_frame, void* stream);
+/* One pass over an encoder level's output x [F*B,H,W,C] (MR_DT_F16: C % 8 == 0, MR_DT_F32: C % 4 == 0; H, W even) that writes both
+ * consumers: pooled [F*B,H/2,W/2,C] = nn.MaxPool2d(2) (monorec_model.py:304-316) and frame_max [B,H,W,C] = the element-wise
+ * max over the F frames (:362-365). */
+int mr_pool_and_frame_max(const void* src, void* pooled, void* frame_max, int dtype, int F, int B, int H, int W, int C,
+                          void* stream);
 /* dst[i] = (half) src[i] for n contiguous fp32 values (used for channels-last feature maps). */
 int mr_cast_f32_to_f16(const float* src, void* dst, long long n, void* stream);
 /* nn.MaxPool2d(2) on NHWC (monorec_model.py:304-316). H and W must be even. */

@@ -211,6 +211,19 @@ def max_over_frames(x, frames):
     return out
 
 
+def pool_and_frame_max(x, frames):
+    """x: [frames*B,H,W,C] -> (maxpool2(x) [frames*B,H/2,W/2,C], max over the frames [B,H,W,C]) in one pass over x."""
+    lib = _lib.load()
+    FB, H, W, Cc = x.shape
+    B = FB // frames
+    pooled = torch.empty(FB, H // 2, W // 2, Cc, device=x.device, dtype=x.dtype)
+    fmax = torch.empty(B, H, W, Cc, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mr_pool_and_frame_max(x.data_ptr(), pooled.data_ptr(), fmax.data_ptr(), _dt(x), frames, B, H, W, Cc, _stream(x)),
+                   "mr_pool_and_frame_max")
+    return pooled, fmax
+
+
 def mask_volume(volume, mask):
     """cost_volume * (1 - cv_mask) on NCHW tensors (model/monorec/monorec_model.py:713)."""
     lib = _lib.load()

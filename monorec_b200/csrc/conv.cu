@@ -397,6 +397,51 @@ __global__ void max_over_frames_f16_kernel(const uint4* __restrict__ src, uint4*
     }
     dst[i] = m;
 }
+// MaskModule encoder, between two levels (monorec_model.py:357-365 with :304-316): the level's output x [F*B,H,W,C] feeds both
+// the element-wise max over the frames (-> decoder skip connection) and the 2x2 max-pool (-> next level).  One pass over x
+// writes both (two kernels read the 268 MB level-0 tensor twice).  VEC = uint4 (8 half) or float4 (4 fp32).
+template <typename VEC, bool HALF>
+__device__ __forceinline__ VEC vmax(const VEC a, const VEC b) {
+    VEC o;
+    if (HALF) {
+        const __half2* ah = reinterpret_cast<const __half2*>(&a);
+        const __half2* bh = reinterpret_cast<const __half2*>(&b);
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __hmax2(ah[k], bh[k]);
+    } else {
+        const float* af = reinterpret_cast<const float*>(&a);
+        const float* bf = reinterpret_cast<const float*>(&b);
+        float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) of[k] = fmaxf(af[k], bf[k]);
+    }
+    return o;
+}
+template <typename VEC, bool HALF>
+__global__ void pool_and_frame_max_kernel(const VEC* __restrict__ src, VEC* __restrict__ pooled, VEC* __restrict__ fmax, int F, int B,
+                                          int H, int W, int CV, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (b, y/2, x/2, channel vector)
+    if (i >= total) return;
+    const int Wo = W / 2, Ho = H / 2;
+    const int c = (int)(i % CV);
+    size_t r = i / CV;
+    const int x = (int)(r % Wo); r /= Wo;
+    const int y = (int)(r % Ho);
+    const size_t b = r / Ho;
+    const size_t frame = (size_t)B * H * W * CV, frame_o = (size_t)B * Ho * Wo * CV;
+    const size_t o00 = ((b * H + 2 * y) * W + 2 * x) * CV + c, oo = ((b * Ho + y) * Wo + x) * CV + c;
+    VEC m[4];
+    for (int f = 0; f < F; ++f) {
+        const VEC* p = src + (size_t)f * frame + o00;
+        const VEC q0 = __ldg(p), q1 = __ldg(p + CV), q2 = __ldg(p + (size_t)W * CV), q3 = __ldg(p + (size_t)W * CV + CV);
+        pooled[(size_t)f * frame_o + oo] = vmax<VEC, HALF>(vmax<VEC, HALF>(q0, q1), vmax<VEC, HALF>(q2, q3));
+        if (f == 0) { m[0] = q0; m[1] = q1; m[2] = q2; m[3] = q3; }
+        else { m[0] = vmax<VEC, HALF>(m[0], q0); m[1] = vmax<VEC, HALF>(m[1], q1); m[2] = vmax<VEC, HALF>(m[2], q2); m[3] = vmax<VEC, HALF>(m[3], q3); }
+    }
+    VEC* d = fmax + o00;
+    d[0] = m[0]; d[CV] = m[1]; d[(size_t)W * CV] = m[2]; d[(size_t)W * CV + CV] = m[3];
+}
 __global__ void cast_f32_to_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n4) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
@@ -425,6 +470,24 @@ extern "C" int mr_max_over_frames_f16(const void* src, void* dst, int F, long lo
     max_over_frames_f16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         static_cast<const uint4*>(src), static_cast<uint4*>(dst), F, n8);
     MR_LAUNCH_CHECK("max_over_frames_f16_kernel");
+    return MR_OK;
+}
+
+extern "C" int mr_pool_and_frame_max(const void* src, void* pooled, void* frame_max, int dtype, int F, int B, int H, int W, int C,
+                                     void* stream) {
+    const int v = dtype == MR_DT_F16 ? 8 : 4;
+    MR_REQUIRE(src && pooled && frame_max && (dtype == MR_DT_F16 || dtype == MR_DT_F32) && F >= 1 && B >= 1 && C >= v && (C % v) == 0 &&
+                   H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0,
+               "mr_pool_and_frame_max: need even H, W and C %% %d == 0 (got F=%d B=%d H=%d W=%d C=%d)", v, F, B, H, W, C);
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / v);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (dtype == MR_DT_F16)
+        pool_and_frame_max_kernel<uint4, true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            static_cast<const uint4*>(src), static_cast<uint4*>(pooled), static_cast<uint4*>(frame_max), F, B, H, W, C / v, total);
+    else
+        pool_and_frame_max_kernel<float4, false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            static_cast<const float4*>(src), static_cast<float4*>(pooled), static_cast<float4*>(frame_max), F, B, H, W, C / v, total);
+    MR_LAUNCH_CHECK("pool_and_frame_max_kernel");
     return MR_OK;
 }
 

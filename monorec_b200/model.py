@@ -24,6 +24,8 @@ __all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "Res
 TRUNK_CUDNN_F16 = os.environ.get("MONOREC_B200_TRUNK", "cudnn_f16").lower() != "cudnn_f32"
 TRUNK_FUSED = os.environ.get("MONOREC_B200_TRUNK_FUSED", "1") != "0"
 # the trunk's 512-channel level (never consumed, see ResnetEncoder._forward_folded) on first use; 0: always computed
+# MaskModule encoder: 2x2 max-pool and max over the frames in one pass over a level's output; 0: two kernels (A/B measurements)
+FUSED_POOL = os.environ.get("MONOREC_B200_FUSED_POOL", "1") != "0"
 TRUNK_LAZY_LEVEL4 = os.environ.get("MONOREC_B200_TRUNK_LAZY_LEVEL4", "1") != "0"
 
 
@@ -327,12 +329,18 @@ class MaskModule(nn.Module):
         if not self.use_cv:
             x.zero_()
         cv_feats = []
+        fused_pool = FUSED_POOL and nF > 1 and H % 16 == 0 and W % 16 == 0   # (one pass writes the pooled tensor and the frame maximum)
         for lvl in range(5):
-            if lvl > 0:
-                x = C.maxpool2(x)
             for layer in P[f"enc{lvl}"]:
                 x = layer([x])
-            cv_feats.append(C.max_over_frames(x, nF))
+            if lvl == 4:
+                cv_feats.append(C.max_over_frames(x, nF))
+            elif fused_pool:
+                x, fm = C.pool_and_frame_max(x, nF)
+                cv_feats.append(fm)
+            else:
+                cv_feats.append(C.max_over_frames(x, nF))
+                x = C.maxpool2(x)
         img = [C.as_nhwc(f, C.act_dtype()) for f in feats_nchw[:4]]
         if not self.use_features:
             img = [torch.zeros_like(t) for t in img]

@@ -89,6 +89,19 @@ def _model_and_sd(gain, seed=7):
     return model.to(DEV).eval(), sd
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_pool_and_frame_max_is_the_two_ops(dtype):
+    """One pass over an encoder level's output = nn.MaxPool2d(2) per frame + element-wise max over the frames, bit for bit."""
+    from monorec_b200 import conv as C
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(3 * 2, 12, 20, 48, generator=g).to(DEV, dtype)                       # 3 frames x batch 2
+    pooled, fmax = C.pool_and_frame_max(x, 3)
+    ref_pool = F.max_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).to(dtype)
+    ref_max = x.view(3, 2, 12, 20, 48).amax(0)
+    assert torch.equal(pooled, ref_pool) and torch.equal(fmax, ref_max)
+    assert torch.equal(pooled, C.maxpool2(x)) and torch.equal(fmax, C.max_over_frames(x, 3))
+
+
 @pytest.mark.parametrize("conv_mode", ["fp32", "tf32"])
 @pytest.mark.parametrize("gain_tag,gain", [("g1", 1.0), ("g07", 0.7)])
 def test_full_model_matches_reference_golden(gain_tag, gain, conv_mode):
