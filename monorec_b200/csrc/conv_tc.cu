@@ -10,13 +10,19 @@
 //     monorec_model.py:372-380, :541-545) is just one tensor map per source;
 //   * the B operand is the matching [Cout x 32] slice of the packed weights (2-D TMA);
 //   * both land in 128-byte-swizzled K-major shared-memory tiles that tcgen05.mma consumes through smem descriptors.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (tcgen05.ld -> bias -> activation -> NHWC store, optional sub-pixel placement).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (tcgen05.ld ->
+// bias -> activation -> NHWC store, optional sub-pixel placement).  The producer and issuer loops run on CONVERGED warps with
+// elect-predicated instructions (see umma_elect): their operands stay in uniform registers, ~7 SASS instructions per MMA.
 // Pipelines: smem full/empty mbarrier ring between TMA and MMA; tmem full/empty mbarriers between MMA and epilogue (the
-// accumulator is double-buffered in TMEM, the kernel is persistent over output tiles).
-// Variants chosen by the host code at the bottom of this file: 64-byte swizzle rows for half sources of <= 32 channels;
-// conv_tc_halo_kernel (resident weights, one input box per tile) for stride-1 layers whose weights fit in shared memory
-// twice per SM.  The epilogue is staged through shared memory (8 pixels x 64 contiguous bytes per store instruction).
+// accumulator is double-buffered in TMEM, the kernels are persistent over output tiles).
+// Two kernels, chosen by the host code at the bottom of this file:
+//   conv_tc_halo_kernel  stride-1 layers: ONE input box per (tile, K chunk) with its halo, every filter tap a shifted
+//                        shared-memory descriptor into it; weights resident in shared memory, or -- when they do not fit
+//                        next to two input stages -- streamed slice by slice through a second ring; 64- or 128-byte rows;
+//   conv_tc_kernel       everything else (strided layers, the sub-pixel phases of Refine / Upconv -- up to four phases share
+//                        one launch): one input box and one weight slice per (tap, K chunk).
+// The epilogue is staged through shared memory (8 pixels x 64 contiguous bytes per store instruction); one-channel heads take
+// a single accumulator column.  K steps that hold only the zero padding behind a source's channels are skipped.
 //
 // Reference being replaced: nn.Conv2d / nn.ConvTranspose2d + bias + LeakyReLU of model/layers.py:289-400 as used by
 // MaskModule / DepthModule (model/monorec/monorec_model.py:287-385, :476-557).
@@ -51,7 +57,6 @@ struct TcArgs {
     int f16, out_f16;              // half sources+weights / half destination
     uint32_t idesc;                // UMMA instruction descriptor
     int row_bytes;                 // bytes of one K chunk row in shared memory = swizzle span: 128, or 64 (half sources, 32-channel chunks)
-    uint64_t desc_hi;              // smem descriptor without the start address (LBO, SBO = 8 rows, version, swizzle mode)
     // tap-refetch kernel: up to 4 "phases" (the sub-pixel convolutions of one Refine / Upconv layer) share one launch; tile
     // index = spatial tile * n_phase + phase, so the phases of a spatial tile run side by side and its input boxes are L2 hits
     int n_phase;
@@ -86,7 +91,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1: unused for swizzled K-major) |
 //   [32,46) stride byte offset >> 4 (distance between 8-row groups) | [46,48) version = 1 | [49,52) base offset |
-//   [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.  Everything but the start address is layer-constant: TcArgs::desc_hi.
+//   [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.  Everything but the start address is layer-constant (desc_hi()).
 // ---- single-lane instructions issued from CONVERGED warp code ---------------------------------------------------------------
 // The producer and MMA warps used to run their loops under `if (lane == 0)`.  Every operand of UTMALDG / UTCHMMA / UTCBAR lives
 // in a uniform register, and inside a divergent region ptxas cannot keep values there: the SASS of the tap loop had ~20
@@ -763,8 +768,6 @@ static int conv2d_nhwc_tc_impl(const mr_conv_desc* desc, int n_phases, int n_pad
     const int esize = f16 ? 2 : 4;
     const int cmult = f16 ? 8 : 4;            // pixel stride must be a multiple of 16 bytes for TMA
     a.row_bytes = kc * (f16 ? 2 : 4);
-    a.desc_hi = ((uint64_t)1 << 16) | ((uint64_t)((8 * a.row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) |
-                ((uint64_t)(a.row_bytes == 128 ? 2 : 4) << 61);   // layout: SWIZZLE_128B = 2, SWIZZLE_64B = 4
     a.kc = kc; a.f16 = f16 ? 1 : 0; a.out_f16 = (d.dst_dtype == MR_DT_F16) ? 1 : 0;
     // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @[4,6); a/b format @[7,10)/[10,13): TF32 = 2,
     // F16 = 0; K-major A and B; N >> 3 @[17,23); M >> 4 @[24,29)
