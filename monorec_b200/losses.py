@@ -74,6 +74,8 @@ def reprojection_errors(depth_prediction, data_dict, automasking=False, use_mono
     B, C, H, W = keyframe.shape
     if C != 3 or tuple(depth_prediction.shape) != (B, 1, H, W):
         raise ValueError(f"reprojection_loss: keyframe {tuple(keyframe.shape)} / depth_prediction {tuple(depth_prediction.shape)}")
+    if depth_prediction.device != keyframe.device:
+        raise ValueError(f"reprojection_loss: depth_prediction on {depth_prediction.device}, keyframe on {keyframe.device}")
     dev = keyframe.device
     f32 = lambda t: t.to(device=dev, dtype=torch.float32).contiguous()   # noqa: E731
     keyframe = f32(keyframe)
