@@ -202,6 +202,9 @@ int mr_max_over_frames_f16(const void* src, void* dst, int F, long long n_per_fr
  * max over the F frames (:362-365). */
 int mr_pool_and_frame_max(const void* src, void* pooled, void* frame_max, int dtype, int F, int B, int H, int W, int C,
                           void* stream);
+/* torchvision resnet18.maxpool = MaxPool2d(3, stride 2, padding 1) (the trunk's stem pool, monorec_model.py:122) on an NHWC /
+ * channels-last tensor: src [B,H,W,C] -> dst [B,(H-1)/2+1,(W-1)/2+1,C]; MR_DT_F16: C % 8 == 0, MR_DT_F32: C % 4 == 0. */
+int mr_maxpool3s2_nhwc(const void* src, void* dst, int dtype, int B, int H, int W, int C, void* stream);
 /* dst[i] = (half) src[i] for n contiguous fp32 values (used for channels-last feature maps). */
 int mr_cast_f32_to_f16(const float* src, void* dst, long long n, void* stream);
 /* nn.MaxPool2d(2) on NHWC (monorec_model.py:304-316). H and W must be even. */

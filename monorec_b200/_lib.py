@@ -45,6 +45,7 @@ SIGNATURES = {
     "mr_maxpool2_nhwc_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mr_max_over_frames_f16": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "mr_pool_and_frame_max": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mr_maxpool3s2_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mr_cast_f32_to_f16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "mr_maxpool2_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mr_max_over_frames": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p]),

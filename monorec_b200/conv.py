@@ -211,6 +211,19 @@ def max_over_frames(x, frames):
     return out
 
 
+def maxpool3s2_channels_last(x):
+    """MaxPool2d(3, stride 2, padding 1) on an NCHW-shaped channels-last tensor (the ResNet stem pool); returns the same kind."""
+    lib = _lib.load()
+    B, Cc, H, W = x.shape
+    xn = x.permute(0, 2, 3, 1)
+    assert xn.is_contiguous()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(B, Ho, Wo, Cc, device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mr_maxpool3s2_nhwc(xn.data_ptr(), out.data_ptr(), _dt(x), B, H, W, Cc, _stream(x)), "mr_maxpool3s2_nhwc")
+    return out.permute(0, 3, 1, 2)
+
+
 def pool_and_frame_max(x, frames):
     """x: [frames*B,H,W,C] -> (maxpool2(x) [frames*B,H/2,W/2,C], max over the frames [B,H,W,C]) in one pass over x."""
     lib = _lib.load()

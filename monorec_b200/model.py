@@ -24,6 +24,8 @@ __all__ = ["MonoRecModel", "CostVolumeModule", "MaskModule", "DepthModule", "Res
 TRUNK_CUDNN_F16 = os.environ.get("MONOREC_B200_TRUNK", "cudnn_f16").lower() != "cudnn_f32"
 TRUNK_FUSED = os.environ.get("MONOREC_B200_TRUNK_FUSED", "1") != "0"
 # the trunk's 512-channel level (never consumed, see ResnetEncoder._forward_folded) on first use; 0: always computed
+# the trunk's 3x3 / stride-2 stem pool on the library's kernel; 0: ATen (A/B measurements)
+STEM_POOL = os.environ.get("MONOREC_B200_STEM_POOL", "1") != "0"
 # MaskModule encoder: 2x2 max-pool and max over the frames in one pass over a level's output; 0: two kernels (A/B measurements)
 FUSED_POOL = os.environ.get("MONOREC_B200_FUSED_POOL", "1") != "0"
 TRUNK_LAZY_LEVEL4 = os.environ.get("MONOREC_B200_TRUNK_LAZY_LEVEL4", "1") != "0"
@@ -185,7 +187,13 @@ class ResnetEncoder(nn.Module):
             return x
         x = conv_relu(x, f["stem"][0], f["stem"][1], tuple(e.conv1.stride), tuple(e.conv1.padding))
         feats = [x]
-        x = e.maxpool(x)
+        mp = e.maxpool
+        if (STEM_POOL and x.is_cuda and x.dtype in (torch.float16, torch.float32) and x.shape[1] % 8 == 0 and
+                x.permute(0, 2, 3, 1).is_contiguous() and isinstance(mp, nn.MaxPool2d) and mp.kernel_size == 3 and mp.stride == 2 and
+                mp.padding == 1 and mp.dilation == 1 and not mp.ceil_mode):
+            x = C.maxpool3s2_channels_last(x)            # (ATen's channels-last max-pool: 75 us for this 33 MB tensor)
+        else:
+            x = mp(x)
         for blocks in f["blocks"][:3]:
             x = run_blocks(x, blocks)
             feats.append(x)
@@ -438,7 +446,15 @@ class DepthModule(nn.Module):
         # cat(cost_volume, keyframe) (:531); when MonoRecModel passes the unmasked volume plus `_cv_mask_for_depth`
         # the (1 - cv_mask) product of :713 is applied during the layout change
         cpad = self._cin0_pad
-        x = (torch.zeros if cpad else torch.empty)(B, H, W, D + 3 + cpad, device=cv.device, dtype=C.act_dtype())
+        # (the pad channels behind cat(cost volume, keyframe) must be zero, not garbage: the buffer is filled with zeros once and
+        # kept -- the two layout kernels below rewrite channels [0, D + 3) on every call, nothing else writes to it)
+        key = (B, H, W, D + 3 + cpad, cv.device, C.act_dtype())
+        if cpad and getattr(self, "_x0_key", None) == key:
+            x = self._x0
+        else:
+            x = (torch.zeros if cpad else torch.empty)(B, H, W, D + 3 + cpad, device=cv.device, dtype=C.act_dtype())
+            if cpad and not torch.cuda.is_current_stream_capturing():
+                self._x0, self._x0_key = x, key
         C.nchw_to_nhwc(cv.to(torch.float32), out=x, out_coff=0, one_minus=data_dict.get("_cv_mask_for_depth"))
         C.nchw_to_nhwc(keyframe.to(torch.float32), out=x, out_coff=D)
         img = [C.as_nhwc(f, C.act_dtype()) for f in feats_nchw[:3]]

@@ -443,3 +443,16 @@ def test_full_model_on_bundled_sample(mode, gain_tag, gain):
         mshare = float((dmask < 5e-3).mean())
         print(f"    mask share within 5e-3: {mshare:.5f}")
         assert dmask.max() < max(2e-2, 4 * n_mask) and mshare > 0.99
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_stem_maxpool_matches_torch(dtype):
+    """MaxPool2d(3, stride 2, padding 1) on channels-last tensors (the ResNet stem pool), bit for bit, odd sizes included."""
+    from monorec_b200 import conv as C
+    g = torch.Generator().manual_seed(11)
+    for (B, Cc, H, W) in [(2, 64, 32, 64), (1, 16, 17, 23), (3, 8, 5, 2)]:
+        x = torch.randn(B, Cc, H, W, generator=g).to(DEV, dtype).contiguous(memory_format=torch.channels_last)
+        out = C.maxpool3s2_channels_last(x)
+        ref = F.max_pool2d(x.float(), 3, 2, 1).to(dtype)
+        assert out.shape == ref.shape and torch.equal(out, ref)
+        assert out.is_contiguous(memory_format=torch.channels_last) or out.shape[2] * out.shape[3] == 1 or Cc == 1
