@@ -446,15 +446,11 @@ class DepthModule(nn.Module):
         # cat(cost_volume, keyframe) (:531); when MonoRecModel passes the unmasked volume plus `_cv_mask_for_depth`
         # the (1 - cv_mask) product of :713 is applied during the layout change
         cpad = self._cin0_pad
-        # (the pad channels behind cat(cost volume, keyframe) must be zero, not garbage: the buffer is filled with zeros once and
-        # kept -- the two layout kernels below rewrite channels [0, D + 3) on every call, nothing else writes to it)
-        key = (B, H, W, D + 3 + cpad, cv.device, C.act_dtype())
-        if cpad and getattr(self, "_x0_key", None) == key:
-            x = self._x0
-        else:
-            x = (torch.zeros if cpad else torch.empty)(B, H, W, D + 3 + cpad, device=cv.device, dtype=C.act_dtype())
-            if cpad and not torch.cuda.is_current_stream_capturing():
-                self._x0, self._x0_key = x, key
+        # (the pad channels behind cat(cost volume, keyframe) must be zero, not garbage; the two layout kernels below write
+        # channels [0, D + 3), so only the pad channels are cleared -- not the whole 84 MB buffer)
+        x = torch.empty(B, H, W, D + 3 + cpad, device=cv.device, dtype=C.act_dtype())
+        if cpad:
+            x[..., D + 3:].zero_()
         C.nchw_to_nhwc(cv.to(torch.float32), out=x, out_coff=0, one_minus=data_dict.get("_cv_mask_for_depth"))
         C.nchw_to_nhwc(keyframe.to(torch.float32), out=x, out_coff=D)
         img = [C.as_nhwc(f, C.act_dtype()) for f in feats_nchw[:3]]
